@@ -1,0 +1,324 @@
+"""ctypes binding of ``libflashckpt.so`` (the C-ABI declared in include/flashckpt.h).
+
+This is the only module that touches the shared library.  There is NO CPU
+fallback: if the library is missing or a call fails, ``NativeError`` is raised
+so a GPU box can never silently run the reference's per-tensor ``copy_`` loop
+(dlrover/python/elastic_agent/torch/ckpt_saver.py:198-231) instead of the
+sm_100a kernels.
+"""
+
+from __future__ import annotations
+
+import ctypes
+import os
+import threading
+from typing import Iterable, List, Optional, Sequence, Tuple
+
+_LIB_NAME = "libflashckpt.so"
+_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", _LIB_NAME)
+
+FC_OK = 0
+FC_EINVAL = -1
+FC_ECUDA = -2
+FC_ENOMEM = -3
+FC_EBUSY = -4
+FC_ENOTREADY = 1
+
+VARIANT_AUTO = 0
+VARIANT_LSU = 1
+VARIANT_TMA = 2
+
+# every symbol include/flashckpt.h declares: (name, restype, argtypes)
+_u64 = ctypes.c_uint64
+_u32 = ctypes.c_uint32
+_vp = ctypes.c_void_p
+_fp = ctypes.POINTER(ctypes.c_float)
+_SIGNATURES = {
+    "fc_version": (ctypes.c_int, []),
+    "fc_strerror": (ctypes.c_char_p, [ctypes.c_int]),
+    "fc_last_error": (ctypes.c_char_p, []),
+    "fc_ctx_create": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(_vp)]),
+    "fc_ctx_destroy": (ctypes.c_int, [_vp]),
+    "fc_arena_reserve": (ctypes.c_int, [_vp, _u64]),
+    "fc_arena_info": (ctypes.c_int, [_vp, ctypes.POINTER(_vp), ctypes.POINTER(_u64)]),
+    "fc_host_register": (ctypes.c_int, [_vp, _vp, _u64, ctypes.c_int]),
+    "fc_host_unregister": (ctypes.c_int, [_vp, _vp]),
+    "fc_plan_create": (
+        ctypes.c_int,
+        [_vp, _u32, ctypes.POINTER(_vp), ctypes.POINTER(_u64), ctypes.POINTER(_u64), _u32,
+         ctypes.POINTER(_vp)],
+    ),
+    "fc_plan_destroy": (ctypes.c_int, [_vp]),
+    "fc_plan_info": (
+        ctypes.c_int,
+        [_vp, ctypes.POINTER(_u64), ctypes.POINTER(_u32), ctypes.POINTER(_u32),
+         ctypes.POINTER(_u64)],
+    ),
+    "fc_pack_async": (ctypes.c_int, [_vp, _vp, ctypes.c_int]),
+    "fc_unpack_async": (ctypes.c_int, [_vp, _vp, ctypes.c_int]),
+    "fc_set_variant": (ctypes.c_int, [_vp, ctypes.c_int]),
+    "fc_set_launch": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int]),
+    "fc_save_async": (ctypes.c_int, [_vp, _vp, _vp, ctypes.POINTER(_u64)]),
+    "fc_save_pack_done": (ctypes.c_int, [_vp, _u64]),
+    "fc_save_poll": (ctypes.c_int, [_vp, _u64]),
+    "fc_save_wait": (ctypes.c_int, [_vp, _u64]),
+    "fc_save_timings": (ctypes.c_int, [_vp, _u64, _fp, _fp, _fp]),
+    "fc_restore_async": (ctypes.c_int, [_vp, _vp, _vp]),
+    "fc_restore_wait": (ctypes.c_int, [_vp]),
+    "fc_restore_timings": (ctypes.c_int, [_vp, _fp, _fp, _fp]),
+}
+
+EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+
+
+class NativeError(RuntimeError):
+    """A libflashckpt call failed (or the library is not built)."""
+
+    def __init__(self, code: int, what: str, detail: str = ""):
+        self.code = code
+        super().__init__(f"{what} failed with code {code}: {detail}")
+
+
+class NativeBusy(NativeError):
+    """FC_EBUSY: the previous save/restore on this context is still in flight."""
+
+
+_lib = None
+_lib_lock = threading.Lock()
+
+
+def library_path() -> str:
+    return _LIB_PATH
+
+
+def load_library():
+    """dlopen libflashckpt.so and type every entry point.  Raises loudly if it
+    has not been built (``python -c 'import __graft_entry__ as g; g.build()'``)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lib_lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(_LIB_PATH):
+            raise NativeError(
+                FC_EINVAL,
+                "load_library",
+                f"{_LIB_PATH} is not built; run __graft_entry__.build() "
+                "(nvcc -gencode arch=compute_100a,code=sm_100a). There is no CPU fallback.",
+            )
+        lib = ctypes.CDLL(_LIB_PATH, mode=ctypes.RTLD_LOCAL)
+        for name, (restype, argtypes) in _SIGNATURES.items():
+            fn = getattr(lib, name)  # AttributeError if the .so is stale
+            fn.restype = restype
+            fn.argtypes = argtypes
+        _lib = lib
+        return _lib
+
+
+def _check(rc: int, what: str) -> int:
+    if rc < 0:
+        lib = load_library()
+        detail = lib.fc_last_error().decode("utf-8", "replace") or lib.fc_strerror(rc).decode()
+        if rc == FC_EBUSY:
+            raise NativeBusy(rc, what, detail)
+        raise NativeError(rc, what, detail)
+    return rc
+
+
+def _stream_ptr(stream) -> Optional[int]:
+    """Accepts None, an int (cudaStream_t) or a torch.cuda.Stream."""
+    if stream is None:
+        return None
+    if isinstance(stream, int):
+        return stream or None
+    return int(stream.cuda_stream) or None
+
+
+class Plan:
+    """Cached descriptor table of one state_dict structure (fc_plan)."""
+
+    def __init__(self, ctx: "Context", handle: int, key):
+        self._ctx = ctx
+        self._h = handle
+        self.key = key
+        lib = load_library()
+        payload, items, runs, end = _u64(), _u32(), _u32(), _u64()
+        _check(
+            lib.fc_plan_info(self._h, ctypes.byref(payload), ctypes.byref(items),
+                             ctypes.byref(runs), ctypes.byref(end)),
+            "fc_plan_info",
+        )
+        self.payload_bytes = payload.value
+        self.n_items = items.value
+        self.n_runs = runs.value
+        self.arena_end = end.value
+
+    @property
+    def handle(self) -> int:
+        if not self._h:
+            raise NativeError(FC_EINVAL, "Plan", "plan already destroyed")
+        return self._h
+
+    def pack(self, stream=None, variant: int = VARIANT_AUTO):
+        _check(load_library().fc_pack_async(self.handle, _stream_ptr(stream), variant),
+               "fc_pack_async")
+
+    def unpack(self, stream=None, variant: int = VARIANT_AUTO):
+        _check(load_library().fc_unpack_async(self.handle, _stream_ptr(stream), variant),
+               "fc_unpack_async")
+
+    def save_async(self, host_ptr: int, compute_stream=None) -> int:
+        ticket = _u64()
+        _check(
+            load_library().fc_save_async(self.handle, host_ptr, _stream_ptr(compute_stream),
+                                         ctypes.byref(ticket)),
+            "fc_save_async",
+        )
+        return ticket.value
+
+    def restore_async(self, host_ptr: int, stream=None):
+        _check(load_library().fc_restore_async(self.handle, host_ptr, _stream_ptr(stream)),
+               "fc_restore_async")
+
+    def destroy(self):
+        if self._h:
+            load_library().fc_plan_destroy(self._h)
+            self._h = 0
+
+    def __del__(self):
+        try:
+            self.destroy()
+        except Exception:
+            pass
+
+
+class Context:
+    """One per (process, device): side stream, events, HBM staging arena."""
+
+    def __init__(self, device: int):
+        lib = load_library()
+        h = _vp()
+        _check(lib.fc_ctx_create(int(device), ctypes.byref(h)), "fc_ctx_create")
+        self._h = h.value
+        self.device = int(device)
+        self._registered = {}
+
+    @property
+    def handle(self) -> int:
+        if not self._h:
+            raise NativeError(FC_EINVAL, "Context", "context already destroyed")
+        return self._h
+
+    # -- arena / host segment ------------------------------------------------
+    def arena_reserve(self, nbytes: int):
+        _check(load_library().fc_arena_reserve(self.handle, int(nbytes)), "fc_arena_reserve")
+
+    def arena_info(self) -> Tuple[int, int]:
+        p, n = _vp(), _u64()
+        _check(load_library().fc_arena_info(self.handle, ctypes.byref(p), ctypes.byref(n)),
+               "fc_arena_info")
+        return (p.value or 0, n.value)
+
+    def host_register(self, host_ptr: int, nbytes: int, prefault_threads: int = 0):
+        _check(
+            load_library().fc_host_register(self.handle, host_ptr, int(nbytes),
+                                            int(prefault_threads)),
+            "fc_host_register",
+        )
+        self._registered[host_ptr] = nbytes
+
+    def host_unregister(self, host_ptr: int):
+        if host_ptr in self._registered:
+            _check(load_library().fc_host_unregister(self.handle, host_ptr),
+                   "fc_host_unregister")
+            self._registered.pop(host_ptr, None)
+
+    # -- plans ----------------------------------------------------------------
+    def plan(self, ptrs: Sequence[int], offsets: Sequence[int], nbytes: Sequence[int],
+             chunk_bytes: int = 0) -> Plan:
+        n = len(ptrs)
+        if not (n == len(offsets) == len(nbytes)):
+            raise NativeError(FC_EINVAL, "plan", "ptrs/offsets/nbytes differ in length")
+        a_ptr = (_vp * max(n, 1))(*[int(p) for p in ptrs])
+        a_off = (_u64 * max(n, 1))(*[int(o) for o in offsets])
+        a_len = (_u64 * max(n, 1))(*[int(b) for b in nbytes])
+        h = _vp()
+        _check(
+            load_library().fc_plan_create(self.handle, n, a_ptr, a_off, a_len, int(chunk_bytes),
+                                          ctypes.byref(h)),
+            "fc_plan_create",
+        )
+        key = (tuple(int(p) for p in ptrs), tuple(int(o) for o in offsets),
+               tuple(int(b) for b in nbytes))
+        return Plan(self, h.value, key)
+
+    # -- tuning ----------------------------------------------------------------
+    def set_variant(self, variant: int):
+        _check(load_library().fc_set_variant(self.handle, int(variant)), "fc_set_variant")
+
+    def set_launch(self, lsu_ctas_per_sm: int = 0, tma_ctas_per_sm: int = 0, tma_stages: int = 0,
+                   tma_tile_bytes: int = 0):
+        _check(
+            load_library().fc_set_launch(self.handle, lsu_ctas_per_sm, tma_ctas_per_sm,
+                                         tma_stages, tma_tile_bytes),
+            "fc_set_launch",
+        )
+
+    # -- save / restore tickets ---------------------------------------------------
+    def save_pack_done(self, ticket: int) -> bool:
+        return _check(load_library().fc_save_pack_done(self.handle, ticket),
+                      "fc_save_pack_done") == FC_OK
+
+    def save_poll(self, ticket: int) -> bool:
+        return _check(load_library().fc_save_poll(self.handle, ticket), "fc_save_poll") == FC_OK
+
+    def save_wait(self, ticket: int):
+        _check(load_library().fc_save_wait(self.handle, ticket), "fc_save_wait")
+
+    def save_timings(self, ticket: int) -> Tuple[float, float, float]:
+        a, b, c = ctypes.c_float(), ctypes.c_float(), ctypes.c_float()
+        _check(
+            load_library().fc_save_timings(self.handle, ticket, ctypes.byref(a), ctypes.byref(b),
+                                           ctypes.byref(c)),
+            "fc_save_timings",
+        )
+        return a.value, b.value, c.value
+
+    def restore_wait(self):
+        _check(load_library().fc_restore_wait(self.handle), "fc_restore_wait")
+
+    def restore_timings(self) -> Tuple[float, float, float]:
+        a, b, c = ctypes.c_float(), ctypes.c_float(), ctypes.c_float()
+        _check(
+            load_library().fc_restore_timings(self.handle, ctypes.byref(a), ctypes.byref(b),
+                                              ctypes.byref(c)),
+            "fc_restore_timings",
+        )
+        return a.value, b.value, c.value
+
+    def destroy(self):
+        if self._h:
+            load_library().fc_ctx_destroy(self._h)
+            self._h = 0
+            self._registered.clear()
+
+    def __del__(self):
+        try:
+            self.destroy()
+        except Exception:
+            pass
+
+
+_contexts = {}
+_ctx_lock = threading.Lock()
+
+
+def get_context(device: int) -> Context:
+    """Process-wide context per device index."""
+    with _ctx_lock:
+        ctx = _contexts.get(device)
+        if ctx is None or not ctx._h:
+            ctx = Context(device)
+            _contexts[device] = ctx
+        return ctx

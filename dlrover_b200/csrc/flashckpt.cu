@@ -1,0 +1,922 @@
+// flashckpt.cu — device engine of the B200 Flash Checkpoint path (sm_100a only).
+//
+// What the reference does on this path (dlrover @ 468d632):
+//   ckpt_saver.py:198-231   per leaf: torch.frombuffer(shm).copy_(gpu_tensor)
+//                           -> one blocking pageable cudaMemcpy per tensor.
+// What this file does instead:
+//   1. a cached descriptor table ("plan") maps every leaf tensor to its byte
+//      offset in the checkpoint segment (reference layout: running sum of
+//      numel*element_size, no padding; ckpt_saver.py:286-301);
+//   2. ONE persistent gather kernel copies all leaves into a contiguous HBM
+//      arena that is a byte image of the segment (pack), HBM-bandwidth bound:
+//      algorithmic traffic 2*S bytes per save;
+//   3. the arena is drained to the (pinned) POSIX shm segment by DMA on a side
+//      stream gated by an event — the training stream only ever waits for (2);
+//   4. restore is the inverse: DMA fill + scatter kernel.
+//
+// Two kernel families, both templated on direction:
+//   fc_copy_lsu : 256-thread CTAs, 128-bit LDG/STG, 4-way unrolled; handles any
+//                 byte alignment: a <16 B head/tail peel, and when source and
+//                 destination are not congruent mod 16 it loads two aligned
+//                 16-B words and byte-funnels them (both sides stay aligned).
+//   fc_copy_tma : one elected thread per CTA drives a ring of cp.async.bulk
+//                 global->shared (mbarrier complete_tx) and shared->global
+//                 (bulk_group) transfers; used for the 16-B congruent bodies.
+//
+// No torch types here; see include/flashckpt.h for the ABI contract.
+
+#include "../../include/flashckpt.h"
+
+#include <cuda_runtime.h>
+#include <pthread.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <sys/mman.h>
+#include <unistd.h>
+
+#include <algorithm>
+#include <new>
+#include <vector>
+
+// ------------------------------------------------------------------ errors --
+
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char* fmt, const char* a = "", const char* b = "") {
+  snprintf(g_err, sizeof(g_err), fmt, a, b);
+  return code;
+}
+
+#define FC_CUDA(call)                                                          \
+  do {                                                                         \
+    cudaError_t _e = (call);                                                   \
+    if (_e != cudaSuccess) return fail(FC_ECUDA, "%s: %s", #call, cudaGetErrorString(_e)); \
+  } while (0)
+
+extern "C" int fc_version(void) { return FC_VERSION; }
+
+extern "C" const char* fc_strerror(int code) {
+  switch (code) {
+    case FC_OK: return "ok";
+    case FC_EINVAL: return "invalid argument";
+    case FC_ECUDA: return "CUDA runtime error";
+    case FC_ENOMEM: return "out of memory";
+    case FC_EBUSY: return "a save/restore is still in flight";
+    case FC_ENOTREADY: return "not ready";
+    default: return "unknown flashckpt error";
+  }
+}
+
+extern "C" const char* fc_last_error(void) { return g_err; }
+
+// --------------------------------------------------------------- work items --
+
+// One work item = one contiguous byte range of one tensor, <= chunk_bytes.
+// 32 bytes so a CTA fetches it with two 16-B loads.
+struct __align__(16) FcItem {
+  uint64_t tptr;    // device address inside the tensor
+  uint64_t aoff;    // byte offset inside the arena (== offset in the shm segment)
+  uint32_t nbytes;  // > 0
+  uint32_t pad0;
+  uint64_t pad1;
+};
+static_assert(sizeof(FcItem) == 32, "FcItem must be 32 bytes");
+
+struct FcRun {  // merged contiguous arena range (drain/fill DMA granularity)
+  uint64_t off;
+  uint64_t len;
+};
+
+constexpr int kLsuThreads = 256;
+constexpr int kLsuUnroll = 4;
+constexpr uint32_t kDefaultChunk = 256u << 10;      // work-item size
+constexpr uint64_t kDmaPiece = 256ull << 20;        // drain/fill memcpy size
+
+// ------------------------------------------------------------ device helpers --
+
+__device__ __forceinline__ uint4 ldg_stream(const uint4* p) {
+  uint4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "l"(p));
+  return v;
+}
+
+__device__ __forceinline__ uint4 ldg_cached(const uint4* p) {
+  uint4 v;
+  asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "l"(p));
+  return v;
+}
+
+__device__ __forceinline__ void stg_stream(uint4* p, const uint4& v) {
+  asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x),
+               "r"(v.y), "r"(v.z), "r"(v.w)
+               : "memory");
+}
+
+// 16 output bytes starting r bytes into the 32-byte little-endian pair (lo,hi).
+// q = r>>2 selects the first 32-bit word, sh = 8*(r&3) the bit shift.
+template <int Q>
+__device__ __forceinline__ uint4 funnel16(const uint4& lo, const uint4& hi, uint32_t sh) {
+  const uint32_t w[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+  uint4 o;
+  o.x = __funnelshift_r(w[Q + 0], w[Q + 1], sh);
+  o.y = __funnelshift_r(w[Q + 1], w[Q + 2], sh);
+  o.z = __funnelshift_r(w[Q + 2], w[Q + 3], sh);
+  o.w = __funnelshift_r(w[Q + 3], w[Q + 4], sh);
+  return o;
+}
+
+// Copy nvec 16-B vectors: dst is 16-B aligned, src = abase + r (abase aligned).
+template <int Q>
+__device__ __forceinline__ void copy_shifted(const uint4* __restrict__ abase,
+                                             uint4* __restrict__ dst, uint32_t nvec,
+                                             uint32_t sh) {
+  constexpr int T = kLsuThreads, U = kLsuUnroll;
+  uint32_t i = threadIdx.x;
+  for (; i + (U - 1) * T < nvec; i += U * T) {
+    uint4 lo[U], hi[U];
+#pragma unroll
+    for (int j = 0; j < U; ++j) {
+      lo[j] = ldg_cached(abase + i + j * T);
+      hi[j] = ldg_cached(abase + i + j * T + 1);
+    }
+#pragma unroll
+    for (int j = 0; j < U; ++j) stg_stream(dst + i + j * T, funnel16<Q>(lo[j], hi[j], sh));
+  }
+  for (; i < nvec; i += T) {
+    uint4 lo = ldg_cached(abase + i), hi = ldg_cached(abase + i + 1);
+    stg_stream(dst + i, funnel16<Q>(lo, hi, sh));
+  }
+}
+
+// CTA-wide copy of n bytes, any alignment on either side.
+__device__ __forceinline__ void copy_range(const uint8_t* __restrict__ src,
+                                           uint8_t* __restrict__ dst, uint32_t n) {
+  constexpr int T = kLsuThreads, U = kLsuUnroll;
+  // head: bring dst to 16-B alignment
+  uint32_t head = (uint32_t)((16u - ((uintptr_t)dst & 15u)) & 15u);
+  if (head > n) head = n;
+  if (threadIdx.x < head) dst[threadIdx.x] = src[threadIdx.x];
+  src += head;
+  dst += head;
+  n -= head;
+  const uint32_t nvec = n >> 4;
+  const uint32_t tail = n & 15u;
+  if (threadIdx.x < tail) {
+    const uint32_t o = (nvec << 4) + threadIdx.x;
+    dst[o] = src[o];
+  }
+  if (nvec == 0) return;
+  const uint32_t r = (uint32_t)((uintptr_t)src & 15u);
+  uint4* __restrict__ d = reinterpret_cast<uint4*>(dst);
+  if (r == 0) {
+    const uint4* __restrict__ s = reinterpret_cast<const uint4*>(src);
+    uint32_t i = threadIdx.x;
+    for (; i + (U - 1) * T < nvec; i += U * T) {
+      uint4 v[U];
+#pragma unroll
+      for (int j = 0; j < U; ++j) v[j] = ldg_stream(s + i + j * T);
+#pragma unroll
+      for (int j = 0; j < U; ++j) stg_stream(d + i + j * T, v[j]);
+    }
+    for (; i < nvec; i += T) stg_stream(d + i, ldg_stream(s + i));
+  } else {
+    // The two aligned words that straddle each output vector: the first starts
+    // r bytes before src, the last ends (16-r) bytes after the body; both share
+    // a 16-B word with at least one valid source byte, so no page is touched
+    // that the source range does not already touch.
+    const uint4* __restrict__ ab = reinterpret_cast<const uint4*>(src - r);
+    const uint32_t sh = (r & 3u) * 8u;
+    switch (r >> 2) {
+      case 0: copy_shifted<0>(ab, d, nvec, sh); break;
+      case 1: copy_shifted<1>(ab, d, nvec, sh); break;
+      case 2: copy_shifted<2>(ab, d, nvec, sh); break;
+      default: copy_shifted<3>(ab, d, nvec, sh); break;
+    }
+  }
+}
+
+// DIR 0: tensors -> arena (pack).  DIR 1: arena -> tensors (unpack).
+template <int DIR>
+__global__ void __launch_bounds__(kLsuThreads)
+fc_copy_lsu(const FcItem* __restrict__ items, uint32_t n_items, uint8_t* __restrict__ arena) {
+  for (uint32_t c = blockIdx.x; c < n_items; c += gridDim.x) {
+    const uint4 a = __ldg(reinterpret_cast<const uint4*>(items + c));
+    const uint4 b = __ldg(reinterpret_cast<const uint4*>(items + c) + 1);
+    uint8_t* t = reinterpret_cast<uint8_t*>(((uint64_t)a.y << 32) | a.x);
+    uint8_t* ar = arena + (((uint64_t)a.w << 32) | a.z);
+    const uint32_t n = b.x;
+    if (DIR == 0)
+      copy_range(t, ar, n);
+    else
+      copy_range(ar, t, n);
+  }
+}
+
+// ---------------------------------------------------------------- TMA kernel --
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "FC_WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra FC_DONE_%=;\n"
+      "bra FC_WAIT_%=;\n"
+      "FC_DONE_%=:\n"
+      "}\n" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t smem_dst, const void* gsrc, uint32_t bytes,
+                                         uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+          "r"(smem_dst),
+      "l"(gsrc), "r"(bytes), "r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void* gdst, uint32_t smem_src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst),
+               "r"(smem_src), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() {
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void bulk_wait_all() {
+  asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
+// Walks the tiles of the items owned by this CTA (items blockIdx.x, +gridDim.x, ...).
+struct TileCursor {
+  const FcItem* items;
+  uint32_t n_items, item, off, n;
+  uint64_t tptr, aoff;
+  __device__ __forceinline__ void fetch() {
+    if (item < n_items) {
+      const uint4 a = __ldg(reinterpret_cast<const uint4*>(items + item));
+      const uint4 b = __ldg(reinterpret_cast<const uint4*>(items + item) + 1);
+      tptr = ((uint64_t)a.y << 32) | a.x;
+      aoff = ((uint64_t)a.w << 32) | a.z;
+      n = b.x;
+    }
+  }
+  __device__ __forceinline__ void init(const FcItem* it, uint32_t cnt) {
+    items = it;
+    n_items = cnt;
+    item = blockIdx.x;
+    off = 0;
+    fetch();
+  }
+  __device__ __forceinline__ bool valid() const { return item < n_items; }
+  __device__ __forceinline__ uint32_t bytes(uint32_t tile) const {
+    const uint32_t left = n - off;
+    return left < tile ? left : tile;
+  }
+  __device__ __forceinline__ void advance(uint32_t tile) {
+    off += tile;
+    if (off >= n) {
+      item += gridDim.x;
+      off = 0;
+      fetch();
+    }
+  }
+};
+
+// Every item handed to this kernel has tptr, aoff (and the arena base) 16-B
+// aligned and nbytes a multiple of 16 — the plan builder guarantees it.
+template <int DIR>
+__global__ void __launch_bounds__(32)
+fc_copy_tma(const FcItem* __restrict__ items, uint32_t n_items, uint8_t* __restrict__ arena,
+            uint32_t tile, uint32_t stages) {
+  extern __shared__ __align__(128) uint8_t fc_smem[];
+  if (threadIdx.x != 0) return;
+  const uint32_t smem_base = smem_u32(fc_smem);
+  const uint32_t bar_base = smem_base + stages * tile;
+  for (uint32_t s = 0; s < stages; ++s) mbar_init(bar_base + 8 * s, 1);
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+
+  TileCursor ld, st;
+  ld.init(items, n_items);
+  st.init(items, n_items);
+
+  auto issue_load = [&](uint32_t stage) {
+    const uint32_t nb = ld.bytes(tile);
+    const void* g = DIR == 0 ? reinterpret_cast<const void*>(ld.tptr + ld.off)
+                             : reinterpret_cast<const void*>(arena + ld.aoff + ld.off);
+    mbar_expect_tx(bar_base + 8 * stage, nb);
+    bulk_g2s(smem_base + stage * tile, g, nb, bar_base + 8 * stage);
+    ld.advance(tile);
+  };
+
+  uint32_t primed = 0;
+  while (primed < stages && ld.valid()) issue_load(primed++);
+
+  for (uint32_t k = 0; st.valid(); ++k) {
+    const uint32_t stage = k % stages;
+    mbar_wait(bar_base + 8 * stage, (k / stages) & 1u);
+    const uint32_t nb = st.bytes(tile);
+    void* g = DIR == 0 ? reinterpret_cast<void*>(arena + st.aoff + st.off)
+                       : reinterpret_cast<void*>(st.tptr + st.off);
+    bulk_s2g(g, smem_base + stage * tile, nb);
+    bulk_commit();
+    st.advance(tile);
+    if (k >= 1 && ld.valid()) {
+      bulk_wait_read<1>();  // store k-1 (and older) no longer reads its stage
+      issue_load((k - 1) % stages);
+    }
+  }
+  bulk_wait_all();
+}
+
+// ----------------------------------------------------------------- host side --
+
+struct fc_ctx {
+  int device = 0;
+  int sm_count = 148;
+  cudaStream_t copy_stream = nullptr;
+  uint8_t* arena = nullptr;
+  uint64_t arena_bytes = 0;
+  // tuning
+  int variant = FC_VARIANT_LSU;
+  int lsu_ctas_per_sm = 4;
+  int tma_ctas_per_sm = 2;
+  int tma_stages = 6;
+  int tma_tile = 16 << 10;
+  // save pipeline state (one in flight)
+  cudaEvent_t ev_pack_start = nullptr, ev_pack_end = nullptr, ev_drain_start = nullptr,
+              ev_drain_end = nullptr;
+  uint64_t ticket = 0;        // last issued
+  bool save_inflight = false; // until observed complete
+  // restore pipeline state
+  cudaEvent_t ev_fill_start = nullptr, ev_fill_end = nullptr, ev_scatter_end = nullptr;
+  bool restore_inflight = false;
+  std::vector<void*> registered;
+};
+
+struct fc_plan {
+  fc_ctx* ctx = nullptr;
+  FcItem* d_all = nullptr;    // every byte, <= chunk pieces (LSU variant)
+  FcItem* d_bulk = nullptr;   // 16-B congruent bodies (TMA variant)
+  FcItem* d_resid = nullptr;  // heads, tails and non-congruent ranges (TMA variant)
+  uint32_t n_all = 0, n_bulk = 0, n_resid = 0;
+  uint64_t payload = 0, arena_end = 0;
+  std::vector<FcRun> runs;
+};
+
+struct DeviceGuard {
+  int prev = -1;
+  bool ok = true;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    if (prev != dev) ok = cudaSetDevice(dev) == cudaSuccess;
+  }
+  ~DeviceGuard() {
+    int cur = -1;
+    if (prev >= 0 && cudaGetDevice(&cur) == cudaSuccess && cur != prev) cudaSetDevice(prev);
+  }
+};
+
+#define FC_GUARD(ctx)                                                      \
+  DeviceGuard _guard((ctx)->device);                                       \
+  if (!_guard.ok) return fail(FC_ECUDA, "cudaSetDevice failed%s%s")
+
+extern "C" int fc_ctx_create(int device, fc_ctx** out) {
+  if (!out || device < 0) return fail(FC_EINVAL, "fc_ctx_create: bad argument%s%s");
+  fc_ctx* c = new (std::nothrow) fc_ctx();
+  if (!c) return fail(FC_ENOMEM, "fc_ctx_create: host alloc%s%s");
+  c->device = device;
+  DeviceGuard g(device);
+  if (!g.ok) {
+    delete c;
+    return fail(FC_ECUDA, "cudaSetDevice failed%s%s");
+  }
+  cudaDeviceProp prop;
+  cudaError_t e = cudaGetDeviceProperties(&prop, device);
+  if (e != cudaSuccess) {
+    delete c;
+    return fail(FC_ECUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+  }
+  c->sm_count = prop.multiProcessorCount;
+  int lo = 0, hi = 0;
+  cudaDeviceGetStreamPriorityRange(&lo, &hi);
+  e = cudaStreamCreateWithPriority(&c->copy_stream, cudaStreamNonBlocking, hi);
+  cudaEvent_t* evs[] = {&c->ev_pack_start, &c->ev_pack_end,  &c->ev_drain_start, &c->ev_drain_end,
+                        &c->ev_fill_start, &c->ev_fill_end,  &c->ev_scatter_end};
+  for (cudaEvent_t* ev : evs)
+    if (e == cudaSuccess) e = cudaEventCreate(ev);
+  if (e != cudaSuccess) {
+    fc_ctx_destroy(c);
+    return fail(FC_ECUDA, "fc_ctx_create: %s", cudaGetErrorString(e));
+  }
+  *out = c;
+  return FC_OK;
+}
+
+extern "C" int fc_ctx_destroy(fc_ctx* c) {
+  if (!c) return FC_OK;
+  DeviceGuard g(c->device);
+  if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
+  for (void* p : c->registered) cudaHostUnregister(p);
+  cudaEvent_t evs[] = {c->ev_pack_start, c->ev_pack_end, c->ev_drain_start, c->ev_drain_end,
+                       c->ev_fill_start, c->ev_fill_end, c->ev_scatter_end};
+  for (cudaEvent_t ev : evs)
+    if (ev) cudaEventDestroy(ev);
+  if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+  if (c->arena) cudaFree(c->arena);
+  delete c;
+  return FC_OK;
+}
+
+static int refresh_inflight(fc_ctx* c) {
+  if (c->save_inflight) {
+    cudaError_t e = cudaEventQuery(c->ev_drain_end);
+    if (e == cudaSuccess)
+      c->save_inflight = false;
+    else if (e != cudaErrorNotReady)
+      return fail(FC_ECUDA, "cudaEventQuery(drain): %s", cudaGetErrorString(e));
+  }
+  if (c->restore_inflight) {
+    cudaError_t e = cudaEventQuery(c->ev_scatter_end);
+    if (e == cudaSuccess)
+      c->restore_inflight = false;
+    else if (e != cudaErrorNotReady)
+      return fail(FC_ECUDA, "cudaEventQuery(scatter): %s", cudaGetErrorString(e));
+  }
+  return FC_OK;
+}
+
+extern "C" int fc_arena_reserve(fc_ctx* c, uint64_t bytes) {
+  if (!c) return fail(FC_EINVAL, "fc_arena_reserve: null ctx%s%s");
+  FC_GUARD(c);
+  if (bytes <= c->arena_bytes) return FC_OK;
+  int rc = refresh_inflight(c);
+  if (rc) return rc;
+  if (c->save_inflight || c->restore_inflight)
+    return fail(FC_EBUSY, "fc_arena_reserve: arena in use%s%s");
+  if (c->arena) {
+    FC_CUDA(cudaFree(c->arena));
+    c->arena = nullptr;
+    c->arena_bytes = 0;
+  }
+  // +32: the shifted load path may read one aligned 16-B word past the end.
+  uint64_t want = ((bytes + 32 + 511) / 512) * 512;
+  cudaError_t e = cudaMalloc(&c->arena, want);
+  if (e != cudaSuccess) {
+    c->arena = nullptr;
+    (void)cudaGetLastError();
+    return fail(FC_ENOMEM, "cudaMalloc(arena): %s", cudaGetErrorString(e));
+  }
+  c->arena_bytes = bytes;
+  return FC_OK;
+}
+
+extern "C" int fc_arena_info(fc_ctx* c, void** dev_ptr, uint64_t* bytes) {
+  if (!c) return fail(FC_EINVAL, "fc_arena_info: null ctx%s%s");
+  if (dev_ptr) *dev_ptr = c->arena;
+  if (bytes) *bytes = c->arena_bytes;
+  return FC_OK;
+}
+
+struct PrefaultJob {
+  uint8_t* p;
+  size_t n;
+};
+
+static void* prefault_worker(void* arg) {
+  PrefaultJob* j = static_cast<PrefaultJob*>(arg);
+#ifdef MADV_POPULATE_WRITE
+  if (madvise(j->p, j->n, MADV_POPULATE_WRITE) == 0) return nullptr;
+#endif
+  // Fallback: read-touch every page (never modifies an attached segment).
+  const long pg = sysconf(_SC_PAGESIZE);
+  volatile uint8_t sink = 0;
+  for (size_t o = 0; o < j->n; o += (size_t)pg) sink ^= j->p[o];
+  (void)sink;
+  return nullptr;
+}
+
+extern "C" int fc_host_register(fc_ctx* c, void* host, uint64_t bytes, int prefault_threads) {
+  if (!c || !host || bytes == 0) return fail(FC_EINVAL, "fc_host_register: bad argument%s%s");
+  FC_GUARD(c);
+  if (prefault_threads > 0) {
+    const long pg = sysconf(_SC_PAGESIZE);
+    int nt = std::min(prefault_threads, 64);
+    uint64_t per = ((bytes / nt + pg - 1) / pg) * pg;
+    if (per == 0) per = pg;
+    std::vector<pthread_t> th;
+    std::vector<PrefaultJob> jobs;
+    jobs.reserve(nt);
+    // mmap'd segments are page aligned; tolerate an unaligned start anyway
+    uint8_t* base = static_cast<uint8_t*>(host);
+    for (uint64_t o = 0; o < bytes; o += per) jobs.push_back({base + o, (size_t)std::min<uint64_t>(per, bytes - o)});
+    th.resize(jobs.size());
+    for (size_t i = 0; i < jobs.size(); ++i)
+      if (pthread_create(&th[i], nullptr, prefault_worker, &jobs[i]) != 0) {
+        prefault_worker(&jobs[i]);
+        th[i] = 0;
+      }
+    for (size_t i = 0; i < jobs.size(); ++i)
+      if (th[i]) pthread_join(th[i], nullptr);
+  }
+  cudaError_t e = cudaHostRegister(host, bytes, cudaHostRegisterPortable);
+  if (e == cudaErrorHostMemoryAlreadyRegistered) {
+    (void)cudaGetLastError();
+    return FC_OK;
+  }
+  if (e != cudaSuccess) {
+    (void)cudaGetLastError();
+    return fail(FC_ECUDA, "cudaHostRegister: %s", cudaGetErrorString(e));
+  }
+  c->registered.push_back(host);
+  return FC_OK;
+}
+
+extern "C" int fc_host_unregister(fc_ctx* c, void* host) {
+  if (!c || !host) return fail(FC_EINVAL, "fc_host_unregister: bad argument%s%s");
+  FC_GUARD(c);
+  auto it = std::find(c->registered.begin(), c->registered.end(), host);
+  if (it == c->registered.end()) return FC_OK;
+  // no DMA may still target the range
+  FC_CUDA(cudaStreamSynchronize(c->copy_stream));
+  c->registered.erase(it);
+  FC_CUDA(cudaHostUnregister(host));
+  return FC_OK;
+}
+
+// Split [off, off+n) so interior boundaries are 128-B aligned in arena space.
+static void split_range(std::vector<FcItem>& out, uint64_t tptr, uint64_t off, uint64_t n,
+                        uint32_t chunk) {
+  uint64_t first = chunk - (off & 127u);
+  while (n > 0) {
+    uint64_t len = std::min<uint64_t>(n, first);
+    FcItem it;
+    it.tptr = tptr;
+    it.aoff = off;
+    it.nbytes = (uint32_t)len;
+    it.pad0 = 0;
+    it.pad1 = 0;
+    out.push_back(it);
+    tptr += len;
+    off += len;
+    n -= len;
+    first = chunk;
+  }
+}
+
+static int upload(FcItem** d, const std::vector<FcItem>& v) {
+  *d = nullptr;
+  if (v.empty()) return FC_OK;
+  cudaError_t e = cudaMalloc(d, v.size() * sizeof(FcItem));
+  if (e != cudaSuccess) {
+    (void)cudaGetLastError();
+    return fail(FC_ENOMEM, "cudaMalloc(plan): %s", cudaGetErrorString(e));
+  }
+  FC_CUDA(cudaMemcpy(*d, v.data(), v.size() * sizeof(FcItem), cudaMemcpyHostToDevice));
+  return FC_OK;
+}
+
+extern "C" int fc_plan_create(fc_ctx* c, uint32_t n, const void* const* dev_ptrs,
+                              const uint64_t* arena_off, const uint64_t* nbytes,
+                              uint32_t chunk_bytes, fc_plan** out) {
+  if (!c || !out || (n && (!dev_ptrs || !arena_off || !nbytes)))
+    return fail(FC_EINVAL, "fc_plan_create: null argument%s%s");
+  if (chunk_bytes == 0) chunk_bytes = kDefaultChunk;
+  if (chunk_bytes < 4096 || (chunk_bytes & 127u) || chunk_bytes > (1u << 30))
+    return fail(FC_EINVAL, "fc_plan_create: chunk_bytes must be a multiple of 128 in [4 KiB, 1 GiB]%s%s");
+  FC_GUARD(c);
+  fc_plan* p = new (std::nothrow) fc_plan();
+  if (!p) return fail(FC_ENOMEM, "fc_plan_create: host alloc%s%s");
+  p->ctx = c;
+
+  // runs + overlap check on the arena side
+  std::vector<FcRun> ranges;
+  ranges.reserve(n);
+  for (uint32_t i = 0; i < n; ++i) {
+    if (nbytes[i] == 0) continue;
+    if (!dev_ptrs[i]) {
+      delete p;
+      return fail(FC_EINVAL, "fc_plan_create: null device pointer for a non-empty tensor%s%s");
+    }
+    if (arena_off[i] + nbytes[i] < arena_off[i]) {
+      delete p;
+      return fail(FC_EINVAL, "fc_plan_create: offset overflow%s%s");
+    }
+    ranges.push_back({arena_off[i], nbytes[i]});
+    p->payload += nbytes[i];
+    p->arena_end = std::max(p->arena_end, arena_off[i] + nbytes[i]);
+  }
+  std::sort(ranges.begin(), ranges.end(),
+            [](const FcRun& a, const FcRun& b) { return a.off < b.off; });
+  for (const FcRun& r : ranges) {
+    if (!p->runs.empty()) {
+      FcRun& last = p->runs.back();
+      if (r.off < last.off + last.len) {
+        delete p;
+        return fail(FC_EINVAL, "fc_plan_create: tensors overlap in the arena%s%s");
+      }
+      if (r.off == last.off + last.len) {
+        last.len += r.len;
+        continue;
+      }
+    }
+    p->runs.push_back(r);
+  }
+
+  std::vector<FcItem> all, bulk, resid;
+  for (uint32_t i = 0; i < n; ++i) {
+    uint64_t nb = nbytes[i];
+    if (nb == 0) continue;
+    uint64_t tp = (uint64_t)(uintptr_t)dev_ptrs[i];
+    uint64_t off = arena_off[i];
+    split_range(all, tp, off, nb, chunk_bytes);
+    if (((tp - off) & 15u) != 0) {  // not congruent mod 16: register-funnel path
+      split_range(resid, tp, off, nb, chunk_bytes);
+      continue;
+    }
+    uint64_t head = std::min<uint64_t>((16u - (off & 15u)) & 15u, nb);
+    if (head) split_range(resid, tp, off, head, chunk_bytes);
+    uint64_t body = (nb - head) & ~15ull;
+    if (body) split_range(bulk, tp + head, off + head, body, chunk_bytes);
+    uint64_t tail = nb - head - body;
+    if (tail) split_range(resid, tp + head + body, off + head + body, tail, chunk_bytes);
+  }
+  if (all.size() > 0xFFFFFFF0ull) {
+    delete p;
+    return fail(FC_EINVAL, "fc_plan_create: too many work items%s%s");
+  }
+  p->n_all = (uint32_t)all.size();
+  p->n_bulk = (uint32_t)bulk.size();
+  p->n_resid = (uint32_t)resid.size();
+  int rc = upload(&p->d_all, all);
+  if (!rc) rc = upload(&p->d_bulk, bulk);
+  if (!rc) rc = upload(&p->d_resid, resid);
+  if (rc) {
+    fc_plan_destroy(p);
+    return rc;
+  }
+  *out = p;
+  return FC_OK;
+}
+
+extern "C" int fc_plan_destroy(fc_plan* p) {
+  if (!p) return FC_OK;
+  DeviceGuard g(p->ctx->device);
+  // the kernels that read the tables may still be queued
+  cudaDeviceSynchronize();
+  if (p->d_all) cudaFree(p->d_all);
+  if (p->d_bulk) cudaFree(p->d_bulk);
+  if (p->d_resid) cudaFree(p->d_resid);
+  delete p;
+  return FC_OK;
+}
+
+extern "C" int fc_plan_info(const fc_plan* p, uint64_t* payload_bytes, uint32_t* n_items,
+                            uint32_t* n_runs, uint64_t* arena_end) {
+  if (!p) return fail(FC_EINVAL, "fc_plan_info: null plan%s%s");
+  if (payload_bytes) *payload_bytes = p->payload;
+  if (n_items) *n_items = p->n_all;
+  if (n_runs) *n_runs = (uint32_t)p->runs.size();
+  if (arena_end) *arena_end = p->arena_end;
+  return FC_OK;
+}
+
+extern "C" int fc_set_variant(fc_ctx* c, int variant) {
+  if (!c || variant < FC_VARIANT_AUTO || variant > FC_VARIANT_TMA)
+    return fail(FC_EINVAL, "fc_set_variant: bad argument%s%s");
+  c->variant = variant == FC_VARIANT_AUTO ? FC_VARIANT_LSU : variant;
+  return FC_OK;
+}
+
+extern "C" int fc_set_launch(fc_ctx* c, int lsu_ctas_per_sm, int tma_ctas_per_sm, int tma_stages,
+                             int tma_tile_bytes) {
+  if (!c) return fail(FC_EINVAL, "fc_set_launch: null ctx%s%s");
+  if (lsu_ctas_per_sm < 0 || lsu_ctas_per_sm > 8 || tma_ctas_per_sm < 0 || tma_ctas_per_sm > 16 ||
+      tma_stages < 0 || tma_stages == 1 || tma_stages > 32 || tma_tile_bytes < 0 ||
+      (tma_tile_bytes & 15) || tma_tile_bytes > (128 << 10))
+    return fail(FC_EINVAL, "fc_set_launch: out of range%s%s");
+  int stages = tma_stages ? tma_stages : c->tma_stages;
+  int tile = tma_tile_bytes ? tma_tile_bytes : c->tma_tile;
+  if ((uint64_t)stages * tile + 8ull * stages > (227u << 10))
+    return fail(FC_EINVAL, "fc_set_launch: ring exceeds 227 KB of shared memory%s%s");
+  if (lsu_ctas_per_sm) c->lsu_ctas_per_sm = lsu_ctas_per_sm;
+  if (tma_ctas_per_sm) c->tma_ctas_per_sm = tma_ctas_per_sm;
+  c->tma_stages = stages;
+  c->tma_tile = tile;
+  return FC_OK;
+}
+
+template <int DIR>
+static int launch_lsu(fc_ctx* c, const FcItem* items, uint32_t n, cudaStream_t s) {
+  if (n == 0) return FC_OK;
+  uint32_t grid = std::min<uint32_t>(n, (uint32_t)(c->sm_count * c->lsu_ctas_per_sm));
+  fc_copy_lsu<DIR><<<grid, kLsuThreads, 0, s>>>(items, n, c->arena);
+  FC_CUDA(cudaGetLastError());
+  return FC_OK;
+}
+
+template <int DIR>
+static int launch_tma(fc_ctx* c, const FcItem* items, uint32_t n, cudaStream_t s) {
+  if (n == 0) return FC_OK;
+  const size_t smem = (size_t)c->tma_stages * c->tma_tile + 8u * c->tma_stages;
+  FC_CUDA(cudaFuncSetAttribute(fc_copy_tma<DIR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)smem));
+  uint32_t grid = std::min<uint32_t>(n, (uint32_t)(c->sm_count * c->tma_ctas_per_sm));
+  fc_copy_tma<DIR><<<grid, 32, smem, s>>>(items, n, c->arena, (uint32_t)c->tma_tile,
+                                           (uint32_t)c->tma_stages);
+  FC_CUDA(cudaGetLastError());
+  return FC_OK;
+}
+
+template <int DIR>
+static int launch_copy(fc_plan* p, cudaStream_t s, int variant) {
+  fc_ctx* c = p->ctx;
+  if (p->arena_end > c->arena_bytes)
+    return fail(FC_EINVAL, "arena smaller than the plan: call fc_arena_reserve first%s%s");
+  if (variant == FC_VARIANT_AUTO) variant = c->variant;
+  if (variant == FC_VARIANT_TMA) {
+    int rc = launch_tma<DIR>(c, p->d_bulk, p->n_bulk, s);
+    if (rc) return rc;
+    return launch_lsu<DIR>(c, p->d_resid, p->n_resid, s);
+  }
+  return launch_lsu<DIR>(c, p->d_all, p->n_all, s);
+}
+
+extern "C" int fc_pack_async(fc_plan* p, void* stream, int variant) {
+  if (!p) return fail(FC_EINVAL, "fc_pack_async: null plan%s%s");
+  FC_GUARD(p->ctx);
+  return launch_copy<0>(p, (cudaStream_t)stream, variant);
+}
+
+extern "C" int fc_unpack_async(fc_plan* p, void* stream, int variant) {
+  if (!p) return fail(FC_EINVAL, "fc_unpack_async: null plan%s%s");
+  FC_GUARD(p->ctx);
+  return launch_copy<1>(p, (cudaStream_t)stream, variant);
+}
+
+extern "C" int fc_save_async(fc_plan* p, void* host_base, void* compute_stream, uint64_t* ticket) {
+  if (!p || (!host_base && p->payload)) return fail(FC_EINVAL, "fc_save_async: null argument%s%s");
+  fc_ctx* c = p->ctx;
+  FC_GUARD(c);
+  int rc = refresh_inflight(c);
+  if (rc) return rc;
+  if (c->save_inflight || c->restore_inflight)
+    return fail(FC_EBUSY, "fc_save_async: previous save/restore still draining%s%s");
+  cudaStream_t cs = (cudaStream_t)compute_stream;
+  FC_CUDA(cudaEventRecord(c->ev_pack_start, cs));
+  rc = launch_copy<0>(p, cs, FC_VARIANT_AUTO);
+  if (rc) return rc;
+  FC_CUDA(cudaEventRecord(c->ev_pack_end, cs));
+  FC_CUDA(cudaStreamWaitEvent(c->copy_stream, c->ev_pack_end, 0));
+  FC_CUDA(cudaEventRecord(c->ev_drain_start, c->copy_stream));
+  uint8_t* hb = static_cast<uint8_t*>(host_base);
+  for (const FcRun& r : p->runs)
+    for (uint64_t o = 0; o < r.len; o += kDmaPiece) {
+      uint64_t len = std::min<uint64_t>(kDmaPiece, r.len - o);
+      FC_CUDA(cudaMemcpyAsync(hb + r.off + o, c->arena + r.off + o, len, cudaMemcpyDeviceToHost,
+                              c->copy_stream));
+    }
+  FC_CUDA(cudaEventRecord(c->ev_drain_end, c->copy_stream));
+  c->save_inflight = true;
+  c->ticket += 1;
+  if (ticket) *ticket = c->ticket;
+  return FC_OK;
+}
+
+static int check_ticket(fc_ctx* c, uint64_t ticket, const char* who) {
+  if (!c) return fail(FC_EINVAL, "%s: null ctx", who);
+  if (ticket == 0 || ticket != c->ticket) return fail(FC_EINVAL, "%s: unknown ticket", who);
+  return FC_OK;
+}
+
+extern "C" int fc_save_pack_done(fc_ctx* c, uint64_t ticket) {
+  int rc = check_ticket(c, ticket, "fc_save_pack_done");
+  if (rc) return rc;
+  FC_GUARD(c);
+  cudaError_t e = cudaEventQuery(c->ev_pack_end);
+  if (e == cudaSuccess) return FC_OK;
+  if (e == cudaErrorNotReady) return FC_ENOTREADY;
+  return fail(FC_ECUDA, "cudaEventQuery(pack): %s", cudaGetErrorString(e));
+}
+
+extern "C" int fc_save_poll(fc_ctx* c, uint64_t ticket) {
+  int rc = check_ticket(c, ticket, "fc_save_poll");
+  if (rc) return rc;
+  FC_GUARD(c);
+  cudaError_t e = cudaEventQuery(c->ev_drain_end);
+  if (e == cudaSuccess) {
+    c->save_inflight = false;
+    return FC_OK;
+  }
+  if (e == cudaErrorNotReady) return FC_ENOTREADY;
+  return fail(FC_ECUDA, "cudaEventQuery(drain): %s", cudaGetErrorString(e));
+}
+
+extern "C" int fc_save_wait(fc_ctx* c, uint64_t ticket) {
+  int rc = check_ticket(c, ticket, "fc_save_wait");
+  if (rc) return rc;
+  FC_GUARD(c);
+  FC_CUDA(cudaEventSynchronize(c->ev_drain_end));
+  c->save_inflight = false;
+  return FC_OK;
+}
+
+extern "C" int fc_save_timings(fc_ctx* c, uint64_t ticket, float* pack_ms, float* drain_ms,
+                               float* total_ms) {
+  int rc = check_ticket(c, ticket, "fc_save_timings");
+  if (rc) return rc;
+  FC_GUARD(c);
+  FC_CUDA(cudaEventSynchronize(c->ev_drain_end));
+  c->save_inflight = false;
+  float t = 0.f;
+  if (pack_ms) {
+    FC_CUDA(cudaEventElapsedTime(&t, c->ev_pack_start, c->ev_pack_end));
+    *pack_ms = t;
+  }
+  if (drain_ms) {
+    FC_CUDA(cudaEventElapsedTime(&t, c->ev_drain_start, c->ev_drain_end));
+    *drain_ms = t;
+  }
+  if (total_ms) {
+    FC_CUDA(cudaEventElapsedTime(&t, c->ev_pack_start, c->ev_drain_end));
+    *total_ms = t;
+  }
+  return FC_OK;
+}
+
+extern "C" int fc_restore_async(fc_plan* p, const void* host_base, void* stream) {
+  if (!p || (!host_base && p->payload)) return fail(FC_EINVAL, "fc_restore_async: null argument%s%s");
+  fc_ctx* c = p->ctx;
+  FC_GUARD(c);
+  int rc = refresh_inflight(c);
+  if (rc) return rc;
+  if (c->save_inflight || c->restore_inflight)
+    return fail(FC_EBUSY, "fc_restore_async: arena busy%s%s");
+  if (p->arena_end > c->arena_bytes)
+    return fail(FC_EINVAL, "arena smaller than the plan: call fc_arena_reserve first%s%s");
+  cudaStream_t s = (cudaStream_t)stream;
+  const uint8_t* hb = static_cast<const uint8_t*>(host_base);
+  FC_CUDA(cudaEventRecord(c->ev_fill_start, c->copy_stream));
+  for (const FcRun& r : p->runs)
+    for (uint64_t o = 0; o < r.len; o += kDmaPiece) {
+      uint64_t len = std::min<uint64_t>(kDmaPiece, r.len - o);
+      FC_CUDA(cudaMemcpyAsync(c->arena + r.off + o, hb + r.off + o, len, cudaMemcpyHostToDevice,
+                              c->copy_stream));
+    }
+  FC_CUDA(cudaEventRecord(c->ev_fill_end, c->copy_stream));
+  FC_CUDA(cudaStreamWaitEvent(s, c->ev_fill_end, 0));
+  rc = launch_copy<1>(p, s, FC_VARIANT_AUTO);
+  if (rc) return rc;
+  FC_CUDA(cudaEventRecord(c->ev_scatter_end, s));
+  c->restore_inflight = true;
+  return FC_OK;
+}
+
+extern "C" int fc_restore_wait(fc_ctx* c) {
+  if (!c) return fail(FC_EINVAL, "fc_restore_wait: null ctx%s%s");
+  FC_GUARD(c);
+  FC_CUDA(cudaEventSynchronize(c->ev_scatter_end));
+  c->restore_inflight = false;
+  return FC_OK;
+}
+
+extern "C" int fc_restore_timings(fc_ctx* c, float* fill_ms, float* scatter_ms, float* total_ms) {
+  if (!c) return fail(FC_EINVAL, "fc_restore_timings: null ctx%s%s");
+  FC_GUARD(c);
+  FC_CUDA(cudaEventSynchronize(c->ev_scatter_end));
+  c->restore_inflight = false;
+  float t = 0.f;
+  if (fill_ms) {
+    FC_CUDA(cudaEventElapsedTime(&t, c->ev_fill_start, c->ev_fill_end));
+    *fill_ms = t;
+  }
+  if (scatter_ms) {
+    FC_CUDA(cudaEventElapsedTime(&t, c->ev_fill_end, c->ev_scatter_end));
+    *scatter_ms = t;
+  }
+  if (total_ms) {
+    FC_CUDA(cudaEventElapsedTime(&t, c->ev_fill_start, c->ev_scatter_end));
+    *total_ms = t;
+  }
+  return FC_OK;
+}

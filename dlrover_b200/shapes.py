@@ -1,0 +1,131 @@
+"""Synthetic state_dict builders with the exact tensor names/shapes of the
+configurations BASELINE.json names (no downloads: checkpointing is value
+agnostic, but values are seeded and non-trivial so corruption shows)."""
+
+from __future__ import annotations
+
+from collections import OrderedDict
+from typing import Dict, Iterator, List, Tuple
+
+import torch
+
+
+def llama3_8b_shapes() -> List[Tuple[str, Tuple[int, ...]]]:
+    """HF LlamaForCausalLM (Llama-3-8B): 291 tensors, 8,030,261,248 params."""
+    h, inter, vocab, layers, kv = 4096, 14336, 128256, 32, 1024
+    out: List[Tuple[str, Tuple[int, ...]]] = [("model.embed_tokens.weight", (vocab, h))]
+    for l in range(layers):
+        p = f"model.layers.{l}."
+        out += [
+            (p + "self_attn.q_proj.weight", (h, h)),
+            (p + "self_attn.k_proj.weight", (kv, h)),
+            (p + "self_attn.v_proj.weight", (kv, h)),
+            (p + "self_attn.o_proj.weight", (h, h)),
+            (p + "mlp.gate_proj.weight", (inter, h)),
+            (p + "mlp.up_proj.weight", (inter, h)),
+            (p + "mlp.down_proj.weight", (h, inter)),
+            (p + "input_layernorm.weight", (h,)),
+            (p + "post_attention_layernorm.weight", (h,)),
+        ]
+    out += [("model.norm.weight", (h,)), ("lm_head.weight", (vocab, h))]
+    return out
+
+
+def gpt2_small_shapes() -> List[Tuple[str, Tuple[int, ...]]]:
+    """nanoGPT defaults (12 layers, 768, vocab 50304, block 1024, bias=True);
+    the tied lm_head appears as its own state_dict entry."""
+    d, L, vocab, block = 768, 12, 50304, 1024
+    out = [("transformer.wte.weight", (vocab, d)), ("transformer.wpe.weight", (block, d))]
+    for l in range(L):
+        p = f"transformer.h.{l}."
+        out += [
+            (p + "ln_1.weight", (d,)), (p + "ln_1.bias", (d,)),
+            (p + "attn.c_attn.weight", (3 * d, d)), (p + "attn.c_attn.bias", (3 * d,)),
+            (p + "attn.c_proj.weight", (d, d)), (p + "attn.c_proj.bias", (d,)),
+            (p + "ln_2.weight", (d,)), (p + "ln_2.bias", (d,)),
+            (p + "mlp.c_fc.weight", (4 * d, d)), (p + "mlp.c_fc.bias", (4 * d,)),
+            (p + "mlp.c_proj.weight", (d, 4 * d)), (p + "mlp.c_proj.bias", (d,)),
+        ]
+    out += [("transformer.ln_f.weight", (d,)), ("transformer.ln_f.bias", (d,)),
+            ("lm_head.weight", (vocab, d))]
+    return out
+
+
+def scale_shapes(shapes, scale: float):
+    """Shrink dim 0 of every >=2-D tensor by `scale` (for CPU-sized parity cases)."""
+    if scale >= 1.0:
+        return list(shapes)
+    out = []
+    for name, shp in shapes:
+        if len(shp) >= 2:
+            shp = (max(1, int(shp[0] * scale)),) + tuple(shp[1:])
+        out.append((name, shp))
+    return out
+
+
+def shard_shapes(shapes, world: int, rank: int):
+    """FSDP-style dim-0 row shard: rank r gets rows [r*ceil(n/w), ...)."""
+    out = []
+    for name, shp in shapes:
+        n = shp[0]
+        per = (n + world - 1) // world
+        lo, hi = min(n, rank * per), min(n, (rank + 1) * per)
+        out.append((name, (hi - lo,) + tuple(shp[1:])))
+    return out
+
+
+def fill_(t: torch.Tensor, seed: int) -> torch.Tensor:
+    """Cheap, seeded, non-trivial bit pattern (device-side, no big randn)."""
+    n = t.numel()
+    if n == 0:
+        return t
+    flat = t.view(-1)
+    if t.dtype in (torch.float32, torch.bfloat16, torch.float16, torch.float64):
+        idx = torch.arange(n, device=t.device, dtype=torch.float32)
+        flat.copy_((torch.sin(idx * 0.001 + seed) * 0.02).to(t.dtype))
+    else:
+        idx = torch.arange(n, device=t.device, dtype=torch.int64)
+        flat.copy_(((idx * 2654435761 + seed) % 251).to(t.dtype))
+    return t
+
+
+def build_state_dict(shapes, dtype=torch.bfloat16, device="cpu", seed=1234, fill=True):
+    sd: "OrderedDict[str, torch.Tensor]" = OrderedDict()
+    for i, (name, shp) in enumerate(shapes):
+        t = torch.empty(shp, dtype=dtype, device=device)
+        if fill:
+            fill_(t, seed + i)
+        sd[name] = t
+    return sd
+
+
+def adamw_state(params: Dict[str, torch.Tensor], seed=99, step_device=None):
+    """optimizer.state_dict() of AdamW after one step: per param a 4-byte fp32
+    `step` scalar + fp32 exp_avg + exp_avg_sq, then non-tensor param_groups.
+    The 4-byte scalars make every following offset only 4-B aligned — the
+    reference layout has no padding (ckpt_saver.py:293-301)."""
+    state = {}
+    for i, (name, p) in enumerate(params.items()):
+        dev = step_device if step_device is not None else p.device
+        state[i] = {
+            "step": torch.tensor(1.0, dtype=torch.float32, device=dev),
+            "exp_avg": fill_(torch.empty(p.shape, dtype=torch.float32, device=p.device), seed + 2 * i),
+            "exp_avg_sq": fill_(torch.empty(p.shape, dtype=torch.float32, device=p.device), seed + 2 * i + 1),
+        }
+    groups = [{"lr": 3e-4, "betas": (0.9, 0.95), "eps": 1e-8, "weight_decay": 0.1,
+               "amsgrad": False, "params": list(range(len(params)))}]
+    return {"state": state, "param_groups": groups}
+
+
+def payload_bytes(sd) -> int:
+    total = 0
+    stack = [sd]
+    while stack:
+        v = stack.pop()
+        if isinstance(v, dict):
+            stack.extend(v.values())
+        elif isinstance(v, list):
+            stack.extend(v)
+        elif torch.is_tensor(v):
+            total += v.numel() * v.element_size()
+    return total

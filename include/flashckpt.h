@@ -1,0 +1,152 @@
+/*
+ * flashckpt.h — C-ABI of libflashckpt.so, the B200 (sm_100a) device engine that
+ * sits UNDER the Flash Checkpoint shared-memory handler.
+ *
+ * The reference (dlrover @ 468d632) has no native boundary on this path: the
+ * whole "serialise a state_dict into host shared memory" step is a Python loop
+ * of blocking per-tensor device->pageable-host copies
+ *   dlrover/python/elastic_agent/torch/ckpt_saver.py:198-231
+ *     (_traverse_copy_to_shm / _write_shared_memory: frombuffer(...).copy_(t))
+ *   dlrover/trainer/torch/flash_checkpoint/fsdp_engine.py:133-155 (_write_item)
+ * and the inverse on restore
+ *   dlrover/python/elastic_agent/torch/ckpt_saver.py:144-161 (_read_tensor_from_buf)
+ *   dlrover/trainer/torch/flash_checkpoint/fsdp_engine.py:250-308 (read_data)
+ *   dlrover/trainer/torch/flash_checkpoint/megatron_dist_ckpt.py:654-683.
+ * Every entry point below replaces (part of) that loop; the comment on each
+ * says which lines.  A reference maintainer binds them with ctypes (see
+ * INTEGRATION.md); no torch / C++ types cross this boundary.
+ *
+ * Conventions
+ *   - every function returns FC_OK (0) or a negative FC_E* code; nothing throws;
+ *     fc_last_error() gives the thread-local detail string (CUDA error text...).
+ *   - the caller owns the tensors and must keep them alive and unmodified until
+ *     the pack kernel of a save has finished (fc_save_pack_done / stream order);
+ *     the library owns the staging arena, its streams/events and host
+ *     registrations.
+ *   - "arena offset" == byte offset inside the checkpoint shared-memory segment
+ *     == TensorMeta.offset of the reference (ckpt_saver.py:286-301): running sum
+ *     of numel*element_size, NO padding.  The arena is a byte image of the
+ *     segment, so the drain is a plain DMA.
+ *   - streams are passed as void* (a cudaStream_t / CUstream, e.g.
+ *     torch.cuda.current_stream().cuda_stream); NULL = legacy default stream.
+ */
+#ifndef FLASHCKPT_H_
+#define FLASHCKPT_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FC_VERSION 100 /* 0.1.0 */
+
+enum {
+  FC_OK = 0,
+  FC_EINVAL = -1,  /* bad argument (null handle, overlapping/oversized range...) */
+  FC_ECUDA = -2,   /* a CUDA runtime call failed; see fc_last_error()            */
+  FC_ENOMEM = -3,  /* host or device allocation failed                           */
+  FC_EBUSY = -4,   /* a save/restore is still in flight on this context          */
+  FC_ENOTREADY = 1 /* poll: work still pending (not an error)                    */
+};
+
+/* kernel variants (fc_set_variant / fc_pack_async 'variant' argument) */
+enum {
+  FC_VARIANT_AUTO = 0, /* library default (the faster one as measured on B200) */
+  FC_VARIANT_LSU = 1,  /* 128-bit LDG/STG register path for everything         */
+  FC_VARIANT_TMA = 2   /* cp.async.bulk global->smem->global ring for the 16-B
+                          congruent bodies + LSU kernel for heads/tails/shifted */
+};
+
+typedef struct fc_ctx fc_ctx;   /* one per (process, device)                    */
+typedef struct fc_plan fc_plan; /* cached descriptor table of one state_dict    */
+
+int fc_version(void);
+const char* fc_strerror(int code);
+const char* fc_last_error(void);
+
+/* ---- context, staging arena, host segment ------------------------------- */
+
+/* Creates the side (copy) stream + events on `device`. */
+int fc_ctx_create(int device, fc_ctx** out);
+int fc_ctx_destroy(fc_ctx* ctx);
+
+/* Grow-only device staging arena (HBM image of the SHM segment).
+ * Replaces nothing in the reference: it is what lets the training stream
+ * resume after an HBM-speed snapshot instead of after the PCIe copy. */
+int fc_arena_reserve(fc_ctx* ctx, uint64_t bytes);
+int fc_arena_info(fc_ctx* ctx, void** dev_ptr, uint64_t* bytes);
+
+/* Pin (cudaHostRegister) a host range the CALLER mapped — the POSIX shm
+ * segment of multi_process.py:696-734 / ckpt_saver.py:164-195 — so the drain
+ * is a true async DMA.  prefault_threads>0 first touches the pages from that
+ * many threads (the reference pays this page-fault cost inside its first
+ * copy_ loop).  Registration is per process; the agent never needs it. */
+int fc_host_register(fc_ctx* ctx, void* host, uint64_t bytes, int prefault_threads);
+int fc_host_unregister(fc_ctx* ctx, void* host);
+
+/* ---- plan: the on-device "serialisation header" -------------------------- */
+
+/* Build the descriptor table for n device tensors (contiguous byte ranges):
+ * tensor i lives at dev_ptrs[i] (nbytes[i] bytes) and is serialised at
+ * arena_off[i].  Ranges must not overlap in the arena.  The table is split
+ * into <= chunk_bytes work items whose interior boundaries are 128-B aligned
+ * in arena space, uploaded once, and reused by every later save/restore of
+ * the same state_dict structure (the reference re-walks the dict and re-plans
+ * nothing either: ckpt_saver.py:307-313).  chunk_bytes==0 -> default. */
+int fc_plan_create(fc_ctx* ctx, uint32_t n, const void* const* dev_ptrs,
+                   const uint64_t* arena_off, const uint64_t* nbytes,
+                   uint32_t chunk_bytes, fc_plan** out);
+int fc_plan_destroy(fc_plan* plan);
+/* total payload bytes, number of work items, number of merged arena runs,
+ * end offset (max arena_off+nbytes) */
+int fc_plan_info(const fc_plan* plan, uint64_t* payload_bytes, uint32_t* n_items,
+                 uint32_t* n_runs, uint64_t* arena_end);
+
+/* ---- device kernels alone (tests, ncu, roofline) ------------------------- */
+
+/* tensors -> arena.  Replaces the body of _write_shared_memory
+ * (ckpt_saver.py:221-231) for all leaves at once, at HBM speed. */
+int fc_pack_async(fc_plan* plan, void* stream, int variant);
+/* arena -> tensors.  Replaces the per-parameter copy_ of the restore paths
+ * (ckpt_saver.py:152-158 + user load_state_dict; fsdp_engine.py:303;
+ * megatron_dist_ckpt.py:683). */
+int fc_unpack_async(fc_plan* plan, void* stream, int variant);
+int fc_set_variant(fc_ctx* ctx, int variant);
+/* tuning knobs for the sweep in bench/ncu runs; 0 keeps the current value */
+int fc_set_launch(fc_ctx* ctx, int lsu_ctas_per_sm, int tma_ctas_per_sm,
+                  int tma_stages, int tma_tile_bytes);
+
+/* ---- save: snapshot + drain ---------------------------------------------- */
+
+/* Enqueue the pack kernel on `compute_stream` (the ONLY work the training
+ * stream waits for), then on the context's copy stream — gated by an event,
+ * never by a host sync — DMA every arena run to host_base+offset in
+ * <= drain_chunk pieces.  host_base should be fc_host_register()-ed; if it is
+ * not the copies still work but are staged by the driver.  One save may be in
+ * flight per context (FC_EBUSY otherwise).  Replaces _traverse_copy_to_shm
+ * (ckpt_saver.py:198-218). */
+int fc_save_async(fc_plan* plan, void* host_base, void* compute_stream,
+                  uint64_t* ticket);
+/* FC_OK when the pack kernel of `ticket` has finished (tensors may change). */
+int fc_save_pack_done(fc_ctx* ctx, uint64_t ticket);
+/* FC_OK when all bytes are in host memory, FC_ENOTREADY while pending. */
+int fc_save_poll(fc_ctx* ctx, uint64_t ticket);
+int fc_save_wait(fc_ctx* ctx, uint64_t ticket);
+/* device-side times of the last completed save: pack kernel, drain DMA, and
+ * first-kernel-start -> last-byte-landed. */
+int fc_save_timings(fc_ctx* ctx, uint64_t ticket, float* pack_ms, float* drain_ms,
+                    float* total_ms);
+
+/* ---- restore: fill + scatter ---------------------------------------------- */
+
+/* DMA host_base+offset -> arena on the copy stream, then scatter
+ * arena -> tensors on `stream` (gated by an event).  Inverse of fc_save_async. */
+int fc_restore_async(fc_plan* plan, const void* host_base, void* stream);
+int fc_restore_wait(fc_ctx* ctx);
+int fc_restore_timings(fc_ctx* ctx, float* fill_ms, float* scatter_ms, float* total_ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FLASHCKPT_H_ */

@@ -1,0 +1,188 @@
+"""GPU parity tests of the raw C-ABI (pack / unpack / save / restore) against the
+numpy oracle (oracle/shm_layout.py).  Bit-exact: this path is a pure byte copy."""
+
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+from dlrover_b200 import _native as native
+from oracle import shm_layout as oracle
+
+pytestmark = pytest.mark.gpu
+
+VARIANTS = [native.VARIANT_LSU, native.VARIANT_TMA]
+
+
+def _arena_bytes(ctx, n):
+    ptr, size = ctx.arena_info()
+    assert size >= n
+    out = torch.empty(n, dtype=torch.uint8, device="cuda")
+    # plain cudaMemcpy D2D through torch's ctypes-free path: wrap the arena
+    # pointer with a uint8 tensor via __cuda_array_interface__
+    class _A:
+        __cuda_array_interface__ = {
+            "shape": (n,), "typestr": "|u1", "data": (ptr, False), "version": 2,
+        }
+    src = torch.as_tensor(_A(), device="cuda")
+    out.copy_(src)
+    torch.cuda.synchronize()
+    return out.cpu().numpy()
+
+
+def _ragged_case(seed, aligned):
+    g = torch.Generator().manual_seed(seed)
+    sizes = [0, 1, 3, 15, 16, 17, 4096, 4100, 65537, 300_001, 1_000_003, 5 << 20]
+    tensors, offsets, off = [], [], 0
+    for i, n in enumerate(sizes):
+        t = torch.randint(0, 256, (n,), dtype=torch.uint8, generator=g).cuda()
+        if aligned and n:
+            off = (off + 15) // 16 * 16
+        tensors.append(t)
+        offsets.append(off)
+        off += n
+    return tensors, offsets, off
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
+@pytest.mark.parametrize("aligned", [True, False])
+@pytest.mark.parametrize("chunk", [4096, 0])
+def test_pack_matches_oracle(cuda_device, variant, aligned, chunk):
+    ctx = native.get_context(0)
+    tensors, offsets, total = _ragged_case(1, aligned)
+    ctx.arena_reserve(total)
+    plan = ctx.plan([t.data_ptr() for t in tensors], offsets, [t.numel() for t in tensors], chunk)
+    assert plan.payload_bytes == sum(t.numel() for t in tensors)
+    plan.pack(torch.cuda.current_stream(), variant)
+    torch.cuda.synchronize()
+    got = _arena_bytes(ctx, total)
+    want = oracle.pack_ranges([oracle.tensor_bytes(t) for t in tensors], offsets, total)
+    # gaps (aligned case) are don't-care: compare only covered bytes
+    for t, o in zip(tensors, offsets):
+        n = t.numel()
+        assert np.array_equal(got[o:o + n], want[o:o + n]), f"range at {o} len {n}"
+    plan.destroy()
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
+def test_source_misaligned_views(cuda_device, variant):
+    """Sources that start at odd byte addresses (views into a bigger buffer):
+    exercises every source/destination congruence class mod 16."""
+    ctx = native.get_context(0)
+    g = torch.Generator().manual_seed(7)
+    base = torch.randint(0, 256, (1 << 20,), dtype=torch.uint8, generator=g).cuda()
+    tensors, offsets, off = [], [], 0
+    for r in range(16):
+        for n in (1, 31, 16 * 1024 + r, 100_000 + 3 * r):
+            start = 1000 * (r + 1) + r
+            tensors.append(base[start:start + n])
+            offsets.append(off)
+            off += n
+    ctx.arena_reserve(off)
+    plan = ctx.plan([t.data_ptr() for t in tensors], offsets, [t.numel() for t in tensors], 4096)
+    plan.pack(None, variant)
+    torch.cuda.synchronize()
+    got = _arena_bytes(ctx, off)
+    want = oracle.pack_ranges([oracle.tensor_bytes(t) for t in tensors], offsets, off)
+    assert np.array_equal(got, want)
+    plan.destroy()
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
+def test_unpack_round_trip(cuda_device, variant):
+    ctx = native.get_context(0)
+    tensors, offsets, total = _ragged_case(3, aligned=False)
+    ctx.arena_reserve(total)
+    ptrs = [t.data_ptr() for t in tensors]
+    lens = [t.numel() for t in tensors]
+    plan = ctx.plan(ptrs, offsets, lens)
+    plan.pack(None, variant)
+    keep = [t.clone() for t in tensors]
+    for t in tensors:
+        t.zero_()
+    plan.unpack(None, variant)
+    torch.cuda.synchronize()
+    for a, b in zip(tensors, keep):
+        assert torch.equal(a, b)
+    plan.destroy()
+
+
+def test_save_and_restore_through_host(cuda_device):
+    """fc_save_async -> host segment == oracle image; fc_restore_async brings it
+    back bit-exact.  Mixed dtypes incl. int64 index tensor and bf16 payload."""
+    ctx = native.get_context(0)
+    g = torch.Generator().manual_seed(11)
+    sd = {
+        "w": (torch.randn(257, 129, generator=g) * 0.02).to(torch.bfloat16).cuda(),
+        "idx": torch.arange(1001, dtype=torch.int64).cuda(),
+        "step": torch.tensor(7.0).cuda(),
+        "m": torch.randn(1001, 33, generator=g).cuda(),
+        "u8": torch.randint(0, 256, (12345,), dtype=torch.uint8, generator=g).cuda(),
+        "empty": torch.empty(0).cuda(),
+    }
+    meta, want = oracle.serialize(sd)
+    metas = oracle.flatten_tensor_metas(meta)
+    leaves = list(sd.values())
+    total = want.size
+    ctx.arena_reserve(total)
+    plan = ctx.plan([t.data_ptr() for t in leaves], [m.offset for m in metas],
+                    [m.numel * m.element_size for m in metas])
+    host = torch.empty(total, dtype=torch.uint8).pin_memory()
+    ticket = plan.save_async(host.data_ptr(), torch.cuda.current_stream())
+    ctx.save_wait(ticket)
+    assert np.array_equal(host.numpy(), want)
+    pack_ms, drain_ms, total_ms = ctx.save_timings(ticket)
+    assert pack_ms > 0 and drain_ms > 0 and total_ms >= pack_ms
+    # restore into zeroed tensors
+    keep = {k: v.clone() for k, v in sd.items()}
+    for v in sd.values():
+        v.zero_()
+    plan.restore_async(host.data_ptr(), torch.cuda.current_stream())
+    ctx.restore_wait()
+    for k in sd:
+        assert torch.equal(sd[k], keep[k]), k
+    plan.destroy()
+
+
+def test_registered_pageable_host(cuda_device):
+    """The drain target the product uses: an mmap'd POSIX shm segment pinned
+    with fc_host_register."""
+    import mmap
+    import os
+    import _posixshmem
+
+    ctx = native.get_context(0)
+    name = f"/fc_test_{os.getpid()}"
+    n = 3 << 20
+    fd = _posixshmem.shm_open(name, os.O_CREAT | os.O_EXCL | os.O_RDWR, mode=0o600)
+    try:
+        os.ftruncate(fd, n)
+        mm = mmap.mmap(fd, n)
+        addr = ctypes.addressof(ctypes.c_char.from_buffer(mm))
+        ctx.host_register(addr, n, prefault_threads=2)
+        t = torch.randint(0, 256, (n - 5,), dtype=torch.uint8).cuda()
+        ctx.arena_reserve(n)
+        plan = ctx.plan([t.data_ptr()], [5], [t.numel()])
+        ticket = plan.save_async(addr, None)
+        ctx.save_wait(ticket)
+        assert np.array_equal(np.frombuffer(mm, dtype=np.uint8)[5:], t.cpu().numpy())
+        ctx.host_unregister(addr)
+        plan.destroy()
+    finally:
+        _posixshmem.shm_unlink(name)
+        os.close(fd)
+
+
+def test_busy_and_errors(cuda_device):
+    ctx = native.get_context(0)
+    t = torch.zeros(1024, dtype=torch.uint8, device="cuda")
+    with pytest.raises(native.NativeError):
+        ctx.plan([t.data_ptr(), t.data_ptr()], [0, 100], [1024, 1024])  # overlap
+    with pytest.raises(native.NativeError):
+        ctx.plan([0], [0], [16])  # null pointer, non-empty
+    ctx.arena_reserve(16)
+    big = ctx.plan([t.data_ptr()], [1 << 40], [1024])
+    with pytest.raises(native.NativeError):
+        big.pack()  # arena smaller than plan
+    big.destroy()
