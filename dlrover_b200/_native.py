@@ -63,6 +63,10 @@ _SIGNATURES = {
     "fc_save_poll": (ctypes.c_int, [_vp, _u64]),
     "fc_save_wait": (ctypes.c_int, [_vp, _u64]),
     "fc_save_timings": (ctypes.c_int, [_vp, _u64, _fp, _fp, _fp]),
+    "fc_host_pack": (
+        ctypes.c_int,
+        [_vp, _u32, ctypes.POINTER(_vp), ctypes.POINTER(_u64), ctypes.POINTER(_u64), ctypes.c_int],
+    ),
     "fc_restore_async": (ctypes.c_int, [_vp, _vp, _vp]),
     "fc_restore_wait": (ctypes.c_int, [_vp]),
     "fc_restore_timings": (ctypes.c_int, [_vp, _fp, _fp, _fp]),
@@ -308,6 +312,19 @@ class Context:
             self.destroy()
         except Exception:
             pass
+
+
+def host_pack(dst_addr: int, ptrs: Sequence[int], offsets: Sequence[int],
+              nbytes: Sequence[int], threads: int = 1):
+    """Multi-threaded memcpy of host-resident ranges into the segment (no GPU)."""
+    n = len(ptrs)
+    if n == 0:
+        return
+    a_ptr = (_vp * n)(*[int(p) for p in ptrs])
+    a_off = (_u64 * n)(*[int(o) for o in offsets])
+    a_len = (_u64 * n)(*[int(b) for b in nbytes])
+    _check(load_library().fc_host_pack(dst_addr, n, a_ptr, a_off, a_len, int(threads)),
+           "fc_host_pack")
 
 
 _contexts = {}

@@ -358,11 +358,12 @@ struct fc_ctx {
   uint8_t* arena = nullptr;
   uint64_t arena_bytes = 0;
   // tuning
-  int variant = FC_VARIANT_LSU;
-  int lsu_ctas_per_sm = 4;
+  // tuning: defaults picked from the B200 sweep in profiles/r01_sweep.md
+  int variant = FC_VARIANT_TMA;
+  int lsu_ctas_per_sm = 2;
   int tma_ctas_per_sm = 2;
-  int tma_stages = 6;
-  int tma_tile = 16 << 10;
+  int tma_stages = 3;
+  int tma_tile = 32 << 10;
   // save pipeline state (one in flight)
   cudaEvent_t ev_pack_start = nullptr, ev_pack_end = nullptr, ev_drain_start = nullptr,
               ev_drain_end = nullptr;
@@ -704,7 +705,7 @@ extern "C" int fc_plan_info(const fc_plan* p, uint64_t* payload_bytes, uint32_t*
 extern "C" int fc_set_variant(fc_ctx* c, int variant) {
   if (!c || variant < FC_VARIANT_AUTO || variant > FC_VARIANT_TMA)
     return fail(FC_EINVAL, "fc_set_variant: bad argument%s%s");
-  c->variant = variant == FC_VARIANT_AUTO ? FC_VARIANT_LSU : variant;
+  c->variant = variant == FC_VARIANT_AUTO ? FC_VARIANT_TMA : variant;
   return FC_OK;
 }
 
@@ -861,6 +862,81 @@ extern "C" int fc_save_timings(fc_ctx* c, uint64_t ticket, float* pack_ms, float
     FC_CUDA(cudaEventElapsedTime(&t, c->ev_pack_start, c->ev_drain_end));
     *total_ms = t;
   }
+  return FC_OK;
+}
+
+// ---- host-resident leaves ---------------------------------------------------
+// CPU tensors inside a state_dict (optimizer step counters, RNG state, a whole
+// CPU model in the gloo/CPU configuration) are already in host memory: they go
+// straight into the segment with a (multi-threaded) memcpy, no device hop.
+
+struct HostJob {
+  uint8_t* dst;
+  const void* const* src;
+  const uint64_t* off;
+  const uint64_t* nbytes;
+  uint64_t first, last;
+  uint64_t skip_first, trim_last;  // byte sub-range of the first / last range
+};
+
+static void* host_pack_worker(void* arg) {
+  HostJob* j = static_cast<HostJob*>(arg);
+  for (uint64_t i = j->first; i < j->last; ++i) {
+    uint64_t lo = (i == j->first) ? j->skip_first : 0;
+    uint64_t hi = (i + 1 == j->last) ? j->trim_last : j->nbytes[i];
+    if (hi > lo)
+      memcpy(j->dst + j->off[i] + lo, static_cast<const uint8_t*>(j->src[i]) + lo, hi - lo);
+  }
+  return nullptr;
+}
+
+extern "C" int fc_host_pack(void* dst_base, uint32_t n, const void* const* src,
+                            const uint64_t* off, const uint64_t* nbytes, int threads) {
+  if (!dst_base || (n && (!src || !off || !nbytes)))
+    return fail(FC_EINVAL, "fc_host_pack: null argument%s%s");
+  uint64_t total = 0;
+  for (uint32_t i = 0; i < n; ++i) {
+    if (nbytes[i] && !src[i]) return fail(FC_EINVAL, "fc_host_pack: null source%s%s");
+    total += nbytes[i];
+  }
+  if (total == 0) return FC_OK;
+  int nt = std::max(1, std::min(threads, 64));
+  if (total < (8ull << 20)) nt = 1;  // not worth a thread
+  // equal BYTE shares: a worker may start/stop in the middle of a range
+  std::vector<HostJob> jobs;
+  uint64_t share = (total + nt - 1) / nt;
+  uint32_t i = 0;
+  uint64_t inner = 0;  // bytes of range i already assigned
+  while (i < n) {
+    HostJob j{static_cast<uint8_t*>(dst_base), src, off, nbytes, i, i, inner, 0};
+    uint64_t need = share;
+    while (i < n && need > 0) {
+      uint64_t left = nbytes[i] - inner;
+      if (left <= need) {
+        need -= left;
+        j.trim_last = nbytes[i];
+        ++i;
+        inner = 0;
+      } else {
+        inner += need;
+        j.trim_last = inner;
+        need = 0;
+        j.last = i + 1;
+        break;
+      }
+      j.last = i;
+    }
+    if (j.last > j.first) jobs.push_back(j);
+  }
+  std::vector<pthread_t> th(jobs.size());
+  for (size_t k = 0; k < jobs.size(); ++k) {
+    if (k + 1 == jobs.size() || pthread_create(&th[k], nullptr, host_pack_worker, &jobs[k]) != 0) {
+      host_pack_worker(&jobs[k]);
+      th[k] = 0;
+    }
+  }
+  for (size_t k = 0; k < jobs.size(); ++k)
+    if (th[k]) pthread_join(th[k], nullptr);
   return FC_OK;
 }
 

@@ -1,0 +1,563 @@
+"""Shared-memory handler: serialises a (nested) state_dict into the node-local
+POSIX shm segment the agent persists from, and reads it back.
+
+Contract (reference @ 468d632, dlrover/python/elastic_agent/torch/ckpt_saver.py):
+  * TensorMeta / CheckpointConfig dataclasses (:88-115) and the config key
+    "_DLORVER_CKPT_CONFIG" (:50; the typo is format);
+  * layout = traversal order of Mapping/list containers, offset = running sum
+    of numel*element_size, NO padding (:118-133, :286-301) — SimpleNet + empty
+    SGD state is exactly 9640 bytes;
+  * segment name "[<run_id>_]ckpt_shm_<local_shard>" (:247-259), meta tree kept
+    in the agent's SharedDict "ckpt_meta_<local_shard>" (:261);
+  * save protocol: writing_shm=True -> meta set -> bytes -> writing_shm=False
+    -> meta set (:303-333); a reader that sees writing_shm gets {} (:343-347);
+  * load returns CPU tensors aliasing the segment (:136-161).
+
+What is different underneath: device-resident leaves are NOT copied one by one
+with blocking pageable cudaMemcpy (:221-231).  They are described once to
+libflashckpt (a cached plan), gathered by one sm_100a kernel into an HBM arena
+on the caller's stream, and drained to the pinned segment by DMA on a side
+stream; `save_state_dict(..., blocking=False)` returns as soon as the kernel is
+enqueued and finishes the protocol from a completion thread.  Host-resident
+leaves go straight into the segment with fc_host_pack.  There is no torch
+fallback for CUDA leaves: a missing library raises.
+"""
+
+from __future__ import annotations
+
+import json
+import os
+import threading
+import time
+from collections.abc import Mapping
+from dataclasses import dataclass
+from datetime import datetime
+from typing import Any, Callable, Dict, List, Optional, Tuple
+
+import torch
+
+from . import _native as native
+from .common.constants import EventReportConstants, NodeEnv
+from .common.log import default_logger as logger
+from .common.multi_process import SharedDict, SharedMemory
+
+DLROVER_CKPT_CONFIG_KEY = "_DLORVER_CKPT_CONFIG"
+
+
+def report_local_event(event_type="", instance="", action="", msg="", labels=None):
+    stamp = datetime.now().strftime("%Y-%m-%d, %H:%M:%S")
+    logger.info(f"[{stamp}][{event_type}][{instance}][{action}][{msg}][{json.dumps(labels or {})}]")
+
+
+class CheckpointSharedObjPrefix:
+    SAVE_STEP_QNAME = "ckpt_lock_rank_"
+    META_NAME = "ckpt_meta_"
+    SHM_NAME = "ckpt_shm_"
+    SHM_LOCK_NAME = "shm_lock_"
+
+
+@dataclass
+class TensorMeta:
+    shape: Tuple[int, ...] = None  # type: ignore
+    dtype: torch.dtype = None  # type: ignore
+    element_size: int = 0
+    numel: int = 0
+    offset: int = 0
+
+
+@dataclass
+class CheckpointConfig:
+    """Per-shard header stored under DLROVER_CKPT_CONFIG_KEY in the meta tree.
+
+    step: global iteration; writing_shm: True while the trainer is filling the
+    segment (a reader must not trust the bytes); paths: state name -> storage
+    path the agent persists that sub-dict to."""
+
+    rank: int = 0
+    group_rank: int = 0
+    world_size: int = 0
+    step: int = 0
+    writing_shm: bool = False
+    paths: Dict[str, str] = None  # type: ignore
+
+
+# ------------------------------------------------------------------- traversal --
+
+
+def _traverse_state_dict(value, visitor: Callable):
+    """Depth-first map over Mapping / list containers (tuples are leaves), dict
+    order kept, fresh containers returned."""
+    if isinstance(value, Mapping):
+        return {k: _traverse_state_dict(v, visitor) for k, v in value.items()}
+    if isinstance(value, list):
+        return [_traverse_state_dict(v, visitor) for v in value]
+    return visitor(value)
+
+
+class _Layout:
+    """Result of one planning walk over a state_dict."""
+
+    __slots__ = ("meta", "total", "device_leaves", "host_leaves", "signature")
+
+    def __init__(self):
+        self.meta: Any = None
+        self.total = 0
+        self.device_leaves: List[Tuple[torch.Tensor, TensorMeta]] = []
+        self.host_leaves: List[Tuple[torch.Tensor, TensorMeta]] = []
+        self.signature: Tuple = ()
+
+
+def plan_layout(state_dict) -> _Layout:
+    """Assign every tensor leaf its byte offset (reference layout) and sort the
+    leaves into device-resident and host-resident."""
+    lay = _Layout()
+    sig = []
+
+    def visit(v):
+        if not torch.is_tensor(v):
+            return v
+        numel, esize = v.numel(), v.element_size()
+        m = TensorMeta(shape=tuple(v.shape), dtype=v.dtype, element_size=esize, numel=numel,
+                       offset=lay.total)
+        lay.total += numel * esize
+        sig.append((m.shape, v.dtype, v.device.type))
+        if numel:
+            (lay.device_leaves if v.is_cuda else lay.host_leaves).append((v, m))
+        return m
+
+    lay.meta = _traverse_state_dict(state_dict, visit)
+    lay.signature = tuple(sig)
+    return lay
+
+
+def _read_tensor_from_buf(value, shm: SharedMemory):
+    if not isinstance(value, TensorMeta):
+        return value
+    if value.numel == 0:
+        return torch.tensor([], dtype=value.dtype)
+    flat = torch.frombuffer(shm.buf, dtype=value.dtype, offset=value.offset, count=value.numel)
+    return flat.reshape(value.shape)
+
+
+def _read_state_dict_from_shm(meta_dict, shm: SharedMemory):
+    return _traverse_state_dict(meta_dict, lambda m: _read_tensor_from_buf(m, shm))
+
+
+def _create_shared_memory(name, create, size=0):
+    """Attach to, or (re)create with the requested size, the named segment."""
+    if not create:
+        try:
+            return SharedMemory(name=name)
+        except FileNotFoundError:
+            return None
+    if size == 0:
+        logger.warning("Cannot create the shared memory with size = 0.")
+        return None
+    try:
+        return SharedMemory(name=name, create=True, size=size)
+    except FileExistsError:
+        old = SharedMemory(name=name)
+        if old.size == size:
+            return old
+        logger.info(f"The old size is {old.size} and create a new memory buffer with size {size}.")
+        old.unlink()
+        old.close()
+        return SharedMemory(name=name, create=True, size=size)
+
+
+def _host_threads() -> int:
+    env = os.getenv("DLROVER_B200_HOST_THREADS", "")
+    if env:
+        return max(1, int(env))
+    return max(1, min(16, (os.cpu_count() or 1) // 2))
+
+
+# -------------------------------------------------------------- device staging --
+
+
+class _DeviceStager:
+    """Owns the libflashckpt context usage for ONE segment: host registration,
+    arena sizing and the cached plan."""
+
+    def __init__(self, device_index: int):
+        self.device_index = device_index
+        self.ctx = native.get_context(device_index)
+        self._registered_addr = 0
+        # most-recent-first; 2 entries so a restore plan does not evict the save plan
+        self._plans: List[native.Plan] = []
+        self.register_seconds = 0.0
+
+    def attach(self, shm: SharedMemory):
+        addr = shm.address
+        if addr == self._registered_addr:
+            return
+        self.detach()
+        t0 = time.time()
+        self.ctx.host_register(addr, shm.size, prefault_threads=_host_threads())
+        self.register_seconds = time.time() - t0
+        self._registered_addr = addr
+        logger.info(
+            f"Pinned the {shm.size / 2**30:.2f} GiB checkpoint segment for DMA "
+            f"in {self.register_seconds:.2f}s.")
+
+    def detach(self):
+        if self._registered_addr:
+            try:
+                self.ctx.host_unregister(self._registered_addr)
+            except native.NativeError as e:
+                logger.warning(f"host_unregister: {e}")
+            self._registered_addr = 0
+
+    def plan_for(self, leaves: List[Tuple[torch.Tensor, TensorMeta]], keepalive: list):
+        ptrs, offs, lens = [], [], []
+        for t, m in leaves:
+            if not t.is_contiguous():
+                # rare (state_dict tensors are contiguous); device-side repack,
+                # kept alive until the pack kernel has consumed it
+                t = t.contiguous()
+                keepalive.append(t)
+            ptrs.append(t.data_ptr())
+            offs.append(m.offset)
+            lens.append(m.numel * m.element_size)
+        key = (tuple(ptrs), tuple(offs), tuple(lens))
+        for i, p in enumerate(self._plans):
+            if p.key == key:
+                if i:
+                    self._plans.insert(0, self._plans.pop(i))
+                return p
+        end = max((o + n for o, n in zip(offs, lens)), default=0)
+        self.ctx.arena_reserve(end)
+        plan = self.ctx.plan(ptrs, offs, lens)
+        self._plans.insert(0, plan)
+        while len(self._plans) > 2:
+            self._plans.pop().destroy()
+        return plan
+
+    def close(self):
+        for p in self._plans:
+            p.destroy()
+        self._plans.clear()
+        self.detach()
+
+
+class PendingSave:
+    """Handle of a save whose drain is still running on the copy stream."""
+
+    def __init__(self, ctx: Optional[native.Context], ticket: int, finish: Callable[[], None],
+                 keepalive: list):
+        self._ctx = ctx
+        self._ticket = ticket
+        self._finish = finish
+        self._keepalive = keepalive
+        self._done = threading.Event()
+        self._error: Optional[BaseException] = None
+        self._lock = threading.Lock()
+        self.timings: Optional[Tuple[float, float, float]] = None
+
+    def _complete(self):
+        """Wait for the DMA, then close the protocol.  Runs exactly once."""
+        with self._lock:
+            if self._done.is_set():
+                return
+            try:
+                if self._ctx is not None:
+                    self._ctx.save_wait(self._ticket)
+                    self.timings = self._ctx.save_timings(self._ticket)
+                self._finish()
+            except BaseException as e:  # surfaced by wait()
+                self._error = e
+                logger.error(f"flash checkpoint drain failed: {e}", exc_info=True)
+            finally:
+                self._keepalive.clear()
+                self._done.set()
+
+    def done(self) -> bool:
+        return self._done.is_set()
+
+    def wait(self, timeout: Optional[float] = None) -> bool:
+        ok = self._done.wait(timeout)
+        if ok and self._error is not None:
+            raise self._error
+        return ok
+
+
+# --------------------------------------------------------------------- handler --
+
+
+class SharedMemoryHandler:
+    """Writes / reads the state dict of one local shard to / from shared memory.
+
+    Args:
+        local_rank: index of the local shard (names the segment and meta dict).
+        host: True on the agent (owns the SharedDict server), False in a
+            training process.
+    """
+
+    def __init__(self, local_rank, host=True):
+        self._buffer_size = 0
+        self._local_rank = local_rank
+        run_id = os.getenv(NodeEnv.TORCHELASTIC_RUN_ID, "")
+        base = CheckpointSharedObjPrefix.SHM_NAME + str(local_rank)
+        self._shm_name = f"{run_id}_{base}" if run_id else base
+        self.shared_memory: Optional[SharedMemory] = None
+        self.metadata = SharedDict(name=CheckpointSharedObjPrefix.META_NAME + str(local_rank),
+                                   create=host)
+        self._need_creation = True
+        self._signature: Optional[Tuple] = None
+        self._stager: Optional[_DeviceStager] = None
+        self._pending: Optional[PendingSave] = None
+        self._master_client = None
+        self.last_timings: Optional[Tuple[float, float, float]] = None
+
+    # -- lifecycle ------------------------------------------------------------------
+    def close(self):
+        self.wait_pending()
+        if self._stager is not None:
+            self._stager.close()
+            self._stager = None
+        if self.shared_memory:
+            self.shared_memory.close()
+
+    def unlink(self):
+        if not self.shared_memory:
+            self.init_shared_memory()  # may have been created by another process
+        if self.shared_memory:
+            self.shared_memory.unlink()
+        if self.metadata:
+            self.metadata.unlink()
+
+    def reset(self):
+        self._need_creation = True
+
+    def init_shared_memory(self, create=False, size=0):
+        self.shared_memory = _create_shared_memory(self._shm_name, create=create, size=size)
+        self._need_creation = False
+
+    # -- pending drain ----------------------------------------------------------------
+    def pending_save(self) -> Optional[PendingSave]:
+        p = self._pending
+        return p if p is not None and not p.done() else None
+
+    def wait_pending(self, timeout: Optional[float] = None) -> bool:
+        p = self._pending
+        if p is None:
+            return True
+        return p.wait(timeout)
+
+    # -- save ---------------------------------------------------------------------------
+    def _ensure_segment(self, lay: _Layout):
+        if self.shared_memory is not None and self.shared_memory.size == lay.total \
+                and not self._need_creation:
+            return
+        if self._stager is not None:
+            self._stager.detach()
+        if self.shared_memory is not None:
+            self.shared_memory.close()
+            self.shared_memory = None
+        self.init_shared_memory(create=True, size=lay.total)
+        self._buffer_size = lay.total
+
+    def _stager_for(self, leaves) -> _DeviceStager:
+        dev = leaves[0][0].device
+        index = dev.index if dev.index is not None else torch.cuda.current_device()
+        for t, _ in leaves:
+            if t.device != dev:
+                raise ValueError(
+                    "all CUDA tensors of one checkpoint shard must live on one device; "
+                    f"got {dev} and {t.device}")
+        if self._stager is None or self._stager.device_index != index:
+            if self._stager is not None:
+                self._stager.close()
+            self._stager = _DeviceStager(index)
+        return self._stager
+
+    def save_state_dict(self, state_dict, blocking: bool = True, stream=None,
+                        on_complete: Optional[Callable[[], None]] = None):
+        """Serialise `state_dict` into the segment.
+
+        blocking=True (the reference's semantics): returns None after every
+        byte is in shared memory and the meta says writing_shm=False.
+        blocking=False: returns a PendingSave right after the gather kernel is
+        enqueued on `stream` (default: the current stream); a completion thread
+        finishes the protocol and then calls `on_complete`.
+        """
+        self.wait_pending()
+        lay = plan_layout(state_dict)
+        if lay.total == 0 and self.shared_memory is None:
+            # nothing but non-tensor leaves: still publish the meta tree
+            lay.total = 0
+        if lay.total > 0:
+            self._ensure_segment(lay)
+        self._signature = lay.signature
+        meta_dict = lay.meta
+        conf: CheckpointConfig = meta_dict[DLROVER_CKPT_CONFIG_KEY]
+        conf.writing_shm = True
+        report_local_event(EventReportConstants.TYPE_INFO, str(conf.rank),
+                           EventReportConstants.ACTION_MEM_CKPT_START, f"step={conf.step}")
+        self.metadata.set(meta_dict)
+
+        if lay.host_leaves:
+            assert self.shared_memory is not None
+            keep = []
+            ptrs, offs, lens = [], [], []
+            for t, m in lay.host_leaves:
+                c = t.detach()
+                if not c.is_contiguous():
+                    c = c.contiguous()
+                keep.append(c)
+                ptrs.append(c.data_ptr())
+                offs.append(m.offset)
+                lens.append(m.numel * m.element_size)
+            native.host_pack(self.shared_memory.address, ptrs, offs, lens, _host_threads())
+            del keep
+
+        def finish():
+            conf.writing_shm = False
+            self.metadata.set(meta_dict)
+            report_local_event(EventReportConstants.TYPE_INFO, str(conf.rank),
+                               EventReportConstants.ACTION_MEM_CKPT_COMPLETE,
+                               f"step={conf.step}")
+            if on_complete is not None:
+                on_complete()
+
+        keepalive: list = []
+        ctx, ticket = None, 0
+        if lay.device_leaves:
+            assert self.shared_memory is not None
+            stager = self._stager_for(lay.device_leaves)
+            stager.attach(self.shared_memory)
+            plan = stager.plan_for(lay.device_leaves, keepalive)
+            if stream is None:
+                stream = torch.cuda.current_stream(stager.device_index)
+            ticket = plan.save_async(self.shared_memory.address, stream)
+            ctx = stager.ctx
+            keepalive.append(state_dict)  # tensors must outlive the gather kernel
+
+        pending = PendingSave(ctx, ticket, finish, keepalive)
+        self._pending = pending
+        if blocking or ctx is None:
+            pending._complete()
+            self.last_timings = pending.timings
+            pending.wait()  # re-raise a drain error
+            return None
+        threading.Thread(target=self._run_completion, args=(pending,), name="fc-drain",
+                         daemon=True).start()
+        return pending
+
+    def _run_completion(self, pending: PendingSave):
+        pending._complete()
+        self.last_timings = pending.timings
+
+    # -- load ---------------------------------------------------------------------------
+    def load_state_dict(self):
+        """Returns the state dict (CPU tensors aliasing the segment), or {} when
+        there is no usable in-memory checkpoint."""
+        self.wait_pending()
+        meta_dict = self.metadata.get()
+        config = meta_dict.get(DLROVER_CKPT_CONFIG_KEY, CheckpointConfig())
+        if not meta_dict or config.writing_shm:
+            return {}
+        if self.shared_memory is None or self._need_creation:
+            self.init_shared_memory(create=False)
+        if not self.shared_memory:
+            return {}
+        report_local_event(EventReportConstants.TYPE_INFO, str(config.rank),
+                           EventReportConstants.ACTION_RESUME_MEM_CKPT_START,
+                           f"step={config.step}")
+        state_dict = _read_state_dict_from_shm(meta_dict, self.shared_memory)
+        report_local_event(EventReportConstants.TYPE_INFO, str(config.rank),
+                           EventReportConstants.ACTION_RESUME_MEM_CKPT_COMPLETE,
+                           f"step={config.step}")
+        return state_dict
+
+    def restore_into(self, target, stream=None, strict: bool = True) -> Dict[str, float]:
+        """Scatter the in-memory checkpoint straight into the live tensors of
+        `target` (same tree structure as what was saved; extra keys on either
+        side raise when strict).  CUDA leaves: one DMA fill of the arena + one
+        scatter kernel; CPU leaves: copied from the segment.  Non-tensor leaves
+        of the checkpoint are returned under "extras" untouched.
+
+        Replaces `sd = load_state_dict(); model.load_state_dict(sd)` (per
+        parameter H2D copies from pageable memory, reference ckpt_saver.py:
+        144-161 + user code)."""
+        self.wait_pending()
+        meta_dict = self.metadata.get()
+        config = meta_dict.get(DLROVER_CKPT_CONFIG_KEY, CheckpointConfig())
+        if not meta_dict or config.writing_shm:
+            raise RuntimeError("no consistent in-memory checkpoint to restore from")
+        if self.shared_memory is None or self._need_creation:
+            self.init_shared_memory(create=False)
+        if not self.shared_memory:
+            raise RuntimeError("the checkpoint segment does not exist")
+
+        device_pairs: List[Tuple[torch.Tensor, TensorMeta]] = []
+        host_pairs: List[Tuple[torch.Tensor, TensorMeta]] = []
+
+        def walk(tgt, meta, path):
+            if isinstance(meta, Mapping):
+                if not isinstance(tgt, Mapping):
+                    raise KeyError(f"{path}: checkpoint has a dict, target has {type(tgt).__name__}")
+                for k, m in meta.items():
+                    if k == DLROVER_CKPT_CONFIG_KEY:
+                        continue
+                    if k not in tgt:
+                        if strict:
+                            raise KeyError(f"{path}{k}: missing in target")
+                        continue
+                    walk(tgt[k], m, f"{path}{k}.")
+                if strict:
+                    extra = [k for k in tgt if k not in meta]
+                    if extra:
+                        raise KeyError(f"{path}: target keys not in checkpoint: {extra}")
+            elif isinstance(meta, list):
+                if not isinstance(tgt, list) or len(tgt) != len(meta):
+                    raise KeyError(f"{path}: list length/type mismatch")
+                for i, m in enumerate(meta):
+                    walk(tgt[i], m, f"{path}{i}.")
+            elif isinstance(meta, TensorMeta):
+                if not torch.is_tensor(tgt):
+                    raise KeyError(f"{path}: checkpoint has a tensor, target has {type(tgt).__name__}")
+                if tuple(tgt.shape) != tuple(meta.shape) or tgt.dtype != meta.dtype:
+                    raise ValueError(
+                        f"{path}: shape/dtype mismatch {tuple(tgt.shape)}/{tgt.dtype} vs "
+                        f"{tuple(meta.shape)}/{meta.dtype}")
+                if meta.numel:
+                    (device_pairs if tgt.is_cuda else host_pairs).append((tgt, meta))
+
+        walk(target, meta_dict, "")
+        stats = {"device_bytes": 0.0, "host_bytes": 0.0, "fill_ms": 0.0, "scatter_ms": 0.0}
+        with torch.no_grad():
+            for t, m in host_pairs:
+                t.copy_(_read_tensor_from_buf(m, self.shared_memory))
+                stats["host_bytes"] += m.numel * m.element_size
+            if device_pairs:
+                for t, _ in device_pairs:
+                    if not t.is_contiguous():
+                        raise ValueError("restore_into needs contiguous CUDA targets")
+                stager = self._stager_for(device_pairs)
+                stager.attach(self.shared_memory)
+                plan = stager.plan_for(device_pairs, [])
+                if stream is None:
+                    stream = torch.cuda.current_stream(stager.device_index)
+                plan.restore_async(self.shared_memory.address, stream)
+                stager.ctx.restore_wait()
+                fill, scatter, _ = stager.ctx.restore_timings()
+                stats["fill_ms"], stats["scatter_ms"] = fill, scatter
+                stats["device_bytes"] = float(plan.payload_bytes)
+        return stats
+
+    # -- queries ------------------------------------------------------------------------
+    def no_checkpoint_state(self):
+        """True when the meta dict holds no config or step 0.  (The agent-side
+        handler maps the segment lazily, so the mapping itself says nothing.)"""
+        config = self.metadata.get().get(DLROVER_CKPT_CONFIG_KEY, None)
+        return config is None or config.step == 0
+
+    def get_checkpoint_config(self, default_config):
+        return self.metadata.get().get(DLROVER_CKPT_CONFIG_KEY, default_config)
+
+    def get_master_client(self):
+        return self._master_client
+
+    def set_master_client(self, client):
+        self._master_client = client

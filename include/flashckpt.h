@@ -138,6 +138,16 @@ int fc_save_wait(fc_ctx* ctx, uint64_t ticket);
 int fc_save_timings(fc_ctx* ctx, uint64_t ticket, float* pack_ms, float* drain_ms,
                     float* total_ms);
 
+/* ---- host-resident leaves --------------------------------------------------- */
+
+/* CPU tensors of a state_dict (optimizer step scalars, RNG state, or the whole
+ * model in the CPU/gloo configuration): range i (nbytes[i] bytes at src[i]) is
+ * memcpy'd to dst_base+off[i], split in equal byte shares over `threads` host
+ * threads.  Needs no GPU.  Replaces the CPU-tensor case of
+ * _write_shared_memory (ckpt_saver.py:221-231). */
+int fc_host_pack(void* dst_base, uint32_t n, const void* const* src, const uint64_t* off,
+                 const uint64_t* nbytes, int threads);
+
 /* ---- restore: fill + scatter ---------------------------------------------- */
 
 /* DMA host_base+offset -> arena on the copy stream, then scatter

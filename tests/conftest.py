@@ -24,3 +24,36 @@ def cuda_device():
     assert torch.cuda.is_available(), "gpu-marked test needs a CUDA device"
     torch.cuda.set_device(0)
     return torch.device("cuda", 0)
+
+
+@pytest.fixture
+def run_env(monkeypatch, tmp_path):
+    """Isolated IPC namespace: unique TORCHELASTIC_RUN_ID (socket dir + shm
+    names), saver hosted in-process (ROLE_NAME=dlrover-trainer)."""
+    import shutil
+    import uuid
+
+    run_id = "t" + uuid.uuid4().hex[:10]
+    monkeypatch.setenv("TORCHELASTIC_RUN_ID", run_id)
+    monkeypatch.setenv("ROLE_NAME", "dlrover-trainer")
+    for k in ("LOCAL_RANK", "RANK", "LOCAL_WORLD_SIZE", "GROUP_RANK", "GROUP_WORLD_SIZE",
+              "NODE_RANK", "NODE_NUM", "WORLD_SIZE"):
+        monkeypatch.delenv(k, raising=False)
+    yield run_id
+    from dlrover_b200.ckpt_saver import AsyncCheckpointSaver
+
+    saver = AsyncCheckpointSaver._saver_instance
+    if saver is not None:
+        try:
+            saver.close()
+        except Exception:
+            pass
+        AsyncCheckpointSaver._saver_instance = None
+    shutil.rmtree(os.path.join("/tmp/ckpt_sock", run_id), ignore_errors=True)
+    import glob
+
+    for f in glob.glob(f"/dev/shm/{run_id}_*"):
+        try:
+            os.unlink(f)
+        except OSError:
+            pass

@@ -1,0 +1,67 @@
+"""The C-ABI library loads without a GPU and exports every symbol that
+include/flashckpt.h declares (no compute calls here)."""
+
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from dlrover_b200 import _native as native
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    text = open(os.path.join(ROOT, "include", "flashckpt.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(fc_[a-z_0-9]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = ctypes.CDLL(native.library_path())
+    names = header_symbols()
+    assert len(names) >= 24
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in flashckpt.h but not exported"
+    assert sorted(native.EXPORTED_SYMBOLS) == names
+
+
+def test_version_and_strerror():
+    lib = native.load_library()
+    assert lib.fc_version() == 100
+    assert lib.fc_strerror(0) == b"ok"
+    assert b"flight" in lib.fc_strerror(native.FC_EBUSY)
+
+
+def test_errors_are_codes_not_crashes():
+    lib = native.load_library()
+    assert lib.fc_arena_reserve(None, 10) == native.FC_EINVAL
+    assert lib.fc_plan_destroy(None) == native.FC_OK
+    assert lib.fc_host_pack(None, 0, None, None, None, 1) == native.FC_EINVAL
+    assert b"fc_host_pack" in lib.fc_last_error()
+
+
+def test_host_pack_needs_no_gpu():
+    rng = np.random.default_rng(3)
+    srcs = [rng.integers(0, 256, size=s, dtype=np.uint8) for s in (0, 1, 4097, 9 << 20, 33)]
+    offs, o = [], 7
+    for s in srcs:
+        offs.append(o)
+        o += s.size
+    for threads in (1, 5):
+        dst = np.zeros(o, dtype=np.uint8)
+        native.host_pack(dst.ctypes.data, [s.ctypes.data if s.size else 0 for s in srcs], offs,
+                         [s.size for s in srcs], threads)
+        for s, f in zip(srcs, offs):
+            assert np.array_equal(dst[f:f + s.size], s)
+        assert not dst[:7].any()
+
+
+def test_missing_gpu_is_loud():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("has a GPU")
+    with pytest.raises(native.NativeError):
+        native.Context(0)

@@ -1,0 +1,82 @@
+"""Pins the oracle (oracle/shm_layout.py + oracle/pack_oracle.c) to the golden
+vectors produced by the reference itself (tests/golden/make_golden.py) and to
+the known-answer values in the reference's tests."""
+
+import ctypes
+import hashlib
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+import fixtures  # noqa: E402
+from oracle import shm_layout as oracle  # noqa: E402
+from tests.util import golden, meta_to_json, strip_config, tree_equal  # noqa: E402
+
+
+@pytest.mark.parametrize("name", list(fixtures.FIXTURES))
+def test_oracle_image_and_meta_match_reference(name):
+    info, image = golden(name)
+    sd = {"model_states": fixtures.FIXTURES[name]()}
+    meta, buf = oracle.serialize(sd)
+    assert buf.size == info["size"]
+    assert hashlib.sha256(buf.tobytes()).hexdigest() == info["sha256"]
+    assert np.array_equal(buf, image)
+    got = meta_to_json(meta, oracle.OracleTensorMeta)
+    assert got == strip_config(info["meta"])
+
+
+def test_known_answer_sizes():
+    # checkpoint_egine_test.py:251-252 ; checkpoint_backup_test.py:91,99
+    for name, size in fixtures.KNOWN_SIZES.items():
+        _, total = oracle.plan_layout({"model_states": fixtures.FIXTURES[name]()})
+        assert total == size
+    # test_ckpt_saver.py:117-124: 10x10 fp32 -> numel 100, element_size 4, offset 0
+    meta, total = oracle.plan_layout({"x": torch.zeros(10, 10)})
+    m = meta["x"]
+    assert (m.numel, m.element_size, m.offset, m.shape) == (100, 4, 0, (10, 10)) and total == 400
+
+
+@pytest.mark.parametrize("name", list(fixtures.FIXTURES))
+def test_oracle_read_back(name):
+    sd = {"model_states": fixtures.FIXTURES[name]()}
+    meta, buf = oracle.serialize(sd)
+    back = oracle.read_image(meta, buf)
+    # non-contiguous inputs come back contiguous but equal
+    assert tree_equal(back, sd)
+
+
+def test_dcp_item_accounting():
+    # fsdp_ckpt_test.py:188-209: a 2x4 fp32 item is 32 B, next offset 32
+    assert oracle.dcp_item_offsets([32, 32, 5]) == [(0, 32), (32, 32), (64, 5)]
+
+
+def _c_oracle():
+    path = os.path.join(os.path.dirname(os.path.dirname(__file__)), "oracle", "_ref",
+                        "libpack_oracle.so")
+    if not os.path.exists(path):
+        import subprocess
+        subprocess.check_call(["make", "-C", os.path.dirname(os.path.dirname(path))])
+    return ctypes.CDLL(path)
+
+
+@pytest.mark.parametrize("threads", [1, 4])
+def test_c_oracle_agrees_with_numpy_oracle(threads):
+    lib = _c_oracle()
+    sd = {"model_states": fixtures.fixture_mixed()}
+    meta, want = oracle.serialize(sd)
+    metas = oracle.flatten_tensor_metas(meta)
+    leaves = []
+    oracle.traverse(sd, lambda v: leaves.append(v) if torch.is_tensor(v) else None)
+    srcs = [oracle.tensor_bytes(t).copy() for t in leaves]
+    n = len(srcs)
+    dst = np.zeros(want.size, dtype=np.uint8)
+    ptrs = (ctypes.c_void_p * n)(*[s.ctypes.data if s.size else None for s in srcs])
+    offs = (ctypes.c_uint64 * n)(*[m.offset for m in metas])
+    lens = (ctypes.c_uint64 * n)(*[s.size for s in srcs])
+    rc = lib.oracle_pack(ctypes.c_void_p(dst.ctypes.data), ctypes.c_uint64(n), ptrs, offs, lens,
+                         ctypes.c_int(threads))
+    assert rc == 0 and np.array_equal(dst, want)
