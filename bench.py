@@ -1,0 +1,503 @@
+#!/usr/bin/env python
+"""bench.py — Flash Checkpoint hot path on B200.
+
+A "step" = one memory checkpoint of this rank's shard: the Llama-3-8B bf16
+state_dict (291 tensors, 16,060,522,496 bytes), resident in HBM, serialised
+into the node's POSIX shared-memory segment in the reference's byte layout.
+
+  value  whole-job checkpoint GB/s through the raw C-ABI (fc_save_async +
+         fc_save_wait): gather kernel + PCIe drain, device-timed, inputs in HBM.
+  e2e    the same metric through the reference-facing API
+         DdpCheckpointer.save_checkpoint(step, sd, storage_type=MEMORY) +
+         wait_memory_save(): shard lock RPC, readiness collective, meta publish
+         (2 pickled SharedDict.set), gather kernel, D2H drain into the HOST
+         shm segment, lock release.  d2h_bytes_per_step = payload; the inputs of
+         this path are device-resident by definition (the model), so h2d is the
+         descriptor table only (first step).
+  stall_ms  what the training loop loses per checkpoint (the other half of
+         BASELINE.json's metric): measured with a synthetic matmul step.
+  roofline  the gather (pack) kernel against the MEASURED copy bandwidth.
+  cpu_baseline / --impl reference: the reference's algorithm (per-tensor
+         blocking device->pageable-shm copy_, oracle/ref_port.py) on the same
+         box and state_dict.
+
+Launch: python bench.py [--gpus N --steps K --warmup W] ; for N>1 under
+torch.distributed.run, one rank per GPU, every rank saves its own 16 GB shard
+(weak scaling, no data-path collective).
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "checkpoint_GBps"
+UNIT = "GB/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--scale", type=float, default=float(os.getenv("BENCH_SCALE", "1.0")),
+                    help="shrink dim 0 of every 2-D tensor (debug only; 1.0 = BASELINE config)")
+    ap.add_argument("--no-stall", action="store_true", help="skip the stall measurement")
+    return ap.parse_args()
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled DURING the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], 0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx = max(mx, float(f[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def dist_env():
+    rank = int(os.getenv("RANK", "0"))
+    local = int(os.getenv("LOCAL_RANK", "0"))
+    world = int(os.getenv("WORLD_SIZE", "1"))
+    return rank, local, world
+
+
+def max_over_ranks(x: float, world: int, device) -> float:
+    if world == 1:
+        return x
+    import torch
+    import torch.distributed as dist
+
+    t = torch.tensor([x], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def sum_over_ranks(x: float, world: int, device) -> float:
+    if world == 1:
+        return x
+    import torch
+    import torch.distributed as dist
+
+    t = torch.tensor([x], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return float(t.item())
+
+
+def barrier_sync(world):
+    import torch
+    import torch.distributed as dist
+
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        return float(json.load(open(p))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (of measured)"
+    except Exception:
+        return 6650.0, "fallback 6.65 TB/s (of fallback)"
+
+
+def ncu_traffic():
+    p = os.path.join(ROOT, "profiles", "pack_kernel_ncu.json")
+    try:
+        return json.load(open(p)).get("dram_bytes_per_launch")
+    except Exception:
+        return None
+
+
+# ---------------------------------------------------------------- reference arm --
+
+
+def run_reference(args):
+    """Times the reference's algorithm (oracle/ref_port.py) on this box."""
+    rank, local, world = dist_env()
+    if rank != 0:
+        return 0
+    import torch
+
+    from dlrover_b200 import shapes
+    from oracle.ref_port import RefPortSaver
+
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    sd = {"model_states": shapes.build_state_dict(
+        shapes.scale_shapes(shapes.llama3_8b_shapes(), args.scale), torch.bfloat16, dev)}
+    S = shapes.payload_bytes(sd)
+    saver = RefPortSaver(f"fc_bench_ref_{os.getpid()}")
+    clocks = ClockSampler(local)
+    try:
+        for _ in range(max(args.warmup, 1)):
+            saver.save(sd)
+        torch.cuda.synchronize()
+        clocks.start()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            saver.save(sd)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+    finally:
+        clk = clocks.stop()
+        saver.close()
+    gbs = S * args.steps / dt / 1e9
+    line = {
+        "impl": "reference", "metric": METRIC, "value": gbs, "unit": UNIT, "n_gpus": 1,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
+        "data": "synthetic",
+        "config": workload_config(S, 1, args.scale),
+        "stall_ms": {"blocking": dt / args.steps * 1e3,
+                     "note": "the reference blocks the training thread for the whole copy"},
+        "cpu_baseline": {"value": gbs, "unit": UNIT, "cores": 1, "kind": "port",
+                         "host_cores": os.cpu_count(),
+                         "sample": f"{args.steps} full saves of the {S / 1e9:.2f} GB state_dict: "
+                                   "per-tensor blocking copy_ into a pageable /dev/shm segment "
+                                   "(oracle/ref_port.py restating ckpt_saver.py:198-231)"},
+        "e2e": {"value": gbs, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0, "clocks": clk,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def workload_config(S, world, scale):
+    return {
+        "workload": "Llama-3-8B bf16 state_dict (HF LlamaForCausalLM names/shapes, 291 tensors), "
+                    "save every step to shared memory; BASELINE.json configs[1]"
+                    + ("" if scale == 1.0 else f" [SCALED x{scale}: not the BASELINE config]"),
+        "payload_bytes_per_rank": S, "ranks": world,
+        "sharding": "every rank saves its own full-size shard to its own segment "
+                    "(DdpCheckpointer local_shard_num=world)",
+        "l2": "inputs (16 GB) and arena (16 GB) are far larger than the 126 MB L2; no flush needed",
+    }
+
+
+# --------------------------------------------------------------------- our arm --
+
+
+def run_ours(args):
+    rank, local, world = dist_env()
+    os.environ.setdefault("TORCHELASTIC_RUN_ID", f"fcbench{os.getppid()}")
+    os.environ.setdefault("DLROVER_LOG_LEVEL", "WARNING")
+    import torch
+    import torch.distributed as dist
+
+    if world > 1:
+        os.environ.setdefault("LOCAL_WORLD_SIZE", str(world))
+        dist.init_process_group("nccl")
+    # create the checkpointer (forks the saver daemon on local rank 0) BEFORE
+    # this process touches CUDA
+    from dlrover_b200 import _native as native
+    from dlrover_b200 import shapes
+    from dlrover_b200.flash_checkpoint.api import DdpCheckpointer, StorageType
+
+    ckpt_dir = f"/tmp/fc_bench_{os.getenv('TORCHELASTIC_RUN_ID')}"
+    ckpt = DdpCheckpointer(ckpt_dir, local_shard_num=world, global_shard_num=world)
+
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    sd = shapes.build_state_dict(shapes.scale_shapes(shapes.llama3_8b_shapes(), args.scale),
+                                 torch.bfloat16, dev)
+    S = shapes.payload_bytes(sd)
+    stream = torch.cuda.current_stream()
+    ctx = native.get_context(local)
+
+    # ---- leg 1: raw C-ABI (value, roofline) ------------------------------------------
+    import ctypes
+    import mmap
+
+    import _posixshmem
+
+    seg_name = f"/fc_bench_raw_{os.getpid()}"
+    fd = _posixshmem.shm_open(seg_name, os.O_CREAT | os.O_EXCL | os.O_RDWR, mode=0o600)
+    os.ftruncate(fd, S)
+    seg = mmap.mmap(fd, S)
+    addr = ctypes.addressof(ctypes.c_char.from_buffer(seg))
+    t0 = time.perf_counter()
+    ctx.host_register(addr, S, prefault_threads=min(16, os.cpu_count() or 1))
+    register_s = time.perf_counter() - t0
+    leaves = list(sd.values())
+    offs, o = [], 0
+    for t in leaves:
+        offs.append(o)
+        o += t.numel() * t.element_size()
+    ctx.arena_reserve(S)
+    plan = ctx.plan([t.data_ptr() for t in leaves], offs,
+                    [t.numel() * t.element_size() for t in leaves])
+
+    def raw_step():
+        tk = plan.save_async(addr, stream)
+        ctx.save_wait(tk)
+        return ctx.save_timings(tk)
+
+    for _ in range(max(args.warmup, 3)):
+        raw_step()
+    clocks = ClockSampler(local)
+    barrier_sync(world)
+    clocks.start()
+    k0, m0 = ctx.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    packs, drains = [], []
+    for _ in range(args.steps):
+        p, d, _tot = raw_step()
+        packs.append(p)
+        drains.append(d)
+    ev1.record(stream)
+    barrier_sync(world)
+    raw_ms = ev0.elapsed_time(ev1)
+    k1, m1 = ctx.launch_count()
+    clk = clocks.stop()
+    raw_ms = max_over_ranks(raw_ms, world, dev)
+    value = S * world * args.steps / raw_ms / 1e6
+    pack_ms = sum(packs) / len(packs)
+    drain_ms = sum(drains) / len(drains)
+    peak, peak_src = measured_peak()
+    achieved = 2 * S / pack_ms / 1e6
+
+    # image check: the segment equals the device bytes (first/last tensors + checksum)
+    import numpy as np
+
+    img = np.frombuffer(seg, dtype=np.uint8)
+    for t, off in ((leaves[0], offs[0]), (leaves[-1], offs[-1]), (leaves[5], offs[5])):
+        n = min(t.numel() * t.element_size(), 1 << 20)
+        want = t.view(-1).view(torch.uint8)[:n].cpu().numpy()
+        assert np.array_equal(img[off:off + n], want), "segment image mismatch"
+    del img
+    plan.destroy()
+    ctx.host_unregister(addr)
+    seg.close()
+    os.close(fd)
+    _posixshmem.shm_unlink(seg_name)
+
+    # ---- leg 2: through the Checkpointer API (e2e) -------------------------------------
+    def api_step(step):
+        ckpt.save_checkpoint(step, sd, storage_type=StorageType.MEMORY)
+        ckpt.wait_memory_save()
+
+    t0 = time.perf_counter()
+    api_step(1)  # creates + pins this rank's segment, builds the plan
+    first_save_s = time.perf_counter() - t0
+    for i in range(max(args.warmup, 3)):
+        api_step(2 + i)
+    barrier_sync(world)
+    k2, _ = ctx.launch_count()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        api_step(100 + i)
+    barrier_sync(world)
+    e2e_ms = (time.perf_counter() - t0) * 1e3
+    k3, _ = ctx.launch_count()
+    e2e_ms = max_over_ranks(e2e_ms, world, dev)
+    e2e = S * world * args.steps / e2e_ms / 1e6
+    api_timings = ckpt.engine.last_save_timings()
+
+    # ---- leg 3: exposed stall with a synthetic training step ----------------------------
+    stall = None
+    if not args.no_stall:
+        stall = measure_stall(ckpt, sd, S, dev, world)
+
+    # ---- leg 4: cpu_baseline (rank 0, N=1 only) ------------------------------------------
+    cpu_base = None
+    if world == 1:
+        cpu_base = measure_cpu_baseline(sd, S)
+
+    if world > 1:
+        dist.barrier()
+    ckpt.engine.close()
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": raw_ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
+            "data": "synthetic", "config": workload_config(S, world, args.scale),
+            "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": e2e_ms / args.steps,
+                    "h2d_bytes_per_step": 0, "d2h_bytes_per_step": S,
+                    "api": "DdpCheckpointer.save_checkpoint(MEMORY)+wait_memory_save",
+                    "first_save_s": first_save_s,
+                    "note": "inputs of this path are the live device-resident parameters; "
+                            "the host buffer is the shm segment the drain fills"},
+            "stall_ms": stall,
+            "roofline": {"bound": "hbm", "kernel": "fc_copy_tma<0> (gather/pack)",
+                         "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": ncu_traffic(),
+                         "algorithmic_bytes_per_launch": 2 * S, "avg_launch_ms": pack_ms,
+                         "peak_source": peak_src},
+            "drain": {"avg_ms": drain_ms, "GBps": S / drain_ms / 1e6, "bound": "PCIe Gen5 x16"},
+            "cpu_baseline": cpu_base,
+            "gpu_launches": (k1 - k0) + (k3 - k2),
+            "dma_copies": m1 - m0,
+            "segment_pin_s": register_s,
+            "api_last_timings_ms": api_timings,
+            "clocks": clk,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def measure_stall(ckpt, sd, S, dev, world):
+    """Synthetic training loop: `inner` bf16 8192^3 matmuls per step on the
+    training stream.  Compare step time without checkpoints, with an async
+    memory checkpoint every `every` steps (ours), and with a blocking one."""
+    import torch
+
+    from dlrover_b200.flash_checkpoint.api import StorageType
+
+    a = torch.randn(8192, 8192, device=dev, dtype=torch.bfloat16)
+    b = torch.randn(8192, 8192, device=dev, dtype=torch.bfloat16) * 0.01
+    inner, rounds = 40, 6
+
+    def train_step():
+        c = a
+        for _ in range(inner):
+            c = torch.mm(c, b)
+        return c
+
+    # size the checkpoint interval so a drain (S over PCIe) always fits in it
+    for _ in range(3):
+        train_step()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(5):
+        train_step()
+    torch.cuda.synchronize()
+    step_s = (time.perf_counter() - t0) / 5
+    drain_s = S / 45e9
+    every = int(drain_s * 1.5 / step_s) + 2
+
+    def loop(save_mode):
+        # save_mode: None | "async" | "blocking"
+        barrier_sync(world)
+        t0 = time.perf_counter()
+        host_in_call, saves = 0.0, 0
+        for i in range(every * rounds):
+            train_step()
+            if save_mode and i % every == every - 1:
+                before = ckpt.engine._cached_step
+                h0 = time.perf_counter()
+                ckpt.save_checkpoint(10_000 + i + (0 if save_mode == "async" else 100_000), sd,
+                                     storage_type=StorageType.MEMORY)
+                if save_mode == "blocking":
+                    ckpt.wait_memory_save()
+                host_in_call += time.perf_counter() - h0
+                saves += int(ckpt.engine._cached_step != before)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        ckpt.wait_memory_save()
+        return dt, host_in_call, saves
+
+    loop(None)
+    base = min(loop(None)[0], loop(None)[0])
+    asy, asy_host, n_a = loop("async")
+    blk, blk_host, n_b = loop("blocking")
+    timings = ckpt.engine.last_save_timings() or (None, None, None)
+    return {
+        "async": max((asy - base) / max(n_a, 1) * 1e3, 0.0),
+        "blocking": (blk - base) / max(n_b, 1) * 1e3,
+        "host_call_ms_async": asy_host / max(n_a, 1) * 1e3,
+        "pack_kernel_ms": timings[0],
+        "train_step_ms": base / (every * rounds) * 1e3,
+        "checkpoint_every_steps": every,
+        "saves_done": [n_a, n_b],
+        "saves_attempted": rounds,
+        "method": f"{every * rounds} synthetic steps of {inner} bf16 8192^3 matmuls, a memory "
+                  f"checkpoint every {every} steps; stall = (loop wall time - wall time of the "
+                  "same loop without checkpoints) / #checkpoints; 'async' = product default "
+                  "(returns after enqueueing the gather kernel), 'blocking' = waits for the "
+                  "drain inside the step like the reference",
+    }
+
+
+def measure_cpu_baseline(sd, S):
+    """Reference algorithm on this box, bounded sample: 2 full saves."""
+    import torch
+
+    from oracle.ref_port import RefPortSaver
+
+    saver = RefPortSaver(f"fc_bench_cpu_{os.getpid()}")
+    wrapped = {"model_states": sd}
+    try:
+        saver.save(wrapped)  # creates + faults the pageable segment
+        torch.cuda.synchronize()
+        n = 2
+        t0 = time.perf_counter()
+        for _ in range(n):
+            saver.save(wrapped)
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / n
+    finally:
+        saver.close()
+    return {"value": S / dt / 1e9, "unit": UNIT, "cores": 1, "host_cores": os.cpu_count(),
+            "kind": "port", "ms_per_step": dt * 1e3,
+            "sample": "2 full saves of the same state_dict through oracle/ref_port.py: "
+                      "per-tensor blocking copy_ device->pageable /dev/shm "
+                      "(restates ckpt_saver.py:198-231); single host thread, as the reference"}
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

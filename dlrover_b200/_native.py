@@ -56,6 +56,7 @@ _SIGNATURES = {
     ),
     "fc_pack_async": (ctypes.c_int, [_vp, _vp, ctypes.c_int]),
     "fc_unpack_async": (ctypes.c_int, [_vp, _vp, ctypes.c_int]),
+    "fc_launch_count": (ctypes.c_int, [_vp, ctypes.POINTER(_u64), ctypes.POINTER(_u64)]),
     "fc_set_variant": (ctypes.c_int, [_vp, ctypes.c_int]),
     "fc_set_launch": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int]),
     "fc_save_async": (ctypes.c_int, [_vp, _vp, _vp, ctypes.POINTER(_u64)]),
@@ -256,6 +257,12 @@ class Context:
         key = (tuple(int(p) for p in ptrs), tuple(int(o) for o in offsets),
                tuple(int(b) for b in nbytes))
         return Plan(self, h.value, key)
+
+    def launch_count(self) -> Tuple[int, int]:
+        k, m = _u64(), _u64()
+        _check(load_library().fc_launch_count(self.handle, ctypes.byref(k), ctypes.byref(m)),
+               "fc_launch_count")
+        return k.value, m.value
 
     # -- tuning ----------------------------------------------------------------
     def set_variant(self, variant: int):

@@ -373,6 +373,8 @@ struct fc_ctx {
   cudaEvent_t ev_fill_start = nullptr, ev_fill_end = nullptr, ev_scatter_end = nullptr;
   bool restore_inflight = false;
   std::vector<void*> registered;
+  // evidence counters: kernels launched / DMA copies enqueued by this context
+  uint64_t n_kernels = 0, n_memcpys = 0;
 };
 
 struct fc_plan {
@@ -702,6 +704,13 @@ extern "C" int fc_plan_info(const fc_plan* p, uint64_t* payload_bytes, uint32_t*
   return FC_OK;
 }
 
+extern "C" int fc_launch_count(fc_ctx* c, uint64_t* kernels, uint64_t* memcpys) {
+  if (!c) return fail(FC_EINVAL, "fc_launch_count: null ctx%s%s");
+  if (kernels) *kernels = c->n_kernels;
+  if (memcpys) *memcpys = c->n_memcpys;
+  return FC_OK;
+}
+
 extern "C" int fc_set_variant(fc_ctx* c, int variant) {
   if (!c || variant < FC_VARIANT_AUTO || variant > FC_VARIANT_TMA)
     return fail(FC_EINVAL, "fc_set_variant: bad argument%s%s");
@@ -733,6 +742,7 @@ static int launch_lsu(fc_ctx* c, const FcItem* items, uint32_t n, cudaStream_t s
   uint32_t grid = std::min<uint32_t>(n, (uint32_t)(c->sm_count * c->lsu_ctas_per_sm));
   fc_copy_lsu<DIR><<<grid, kLsuThreads, 0, s>>>(items, n, c->arena);
   FC_CUDA(cudaGetLastError());
+  c->n_kernels += 1;
   return FC_OK;
 }
 
@@ -746,6 +756,7 @@ static int launch_tma(fc_ctx* c, const FcItem* items, uint32_t n, cudaStream_t s
   fc_copy_tma<DIR><<<grid, 32, smem, s>>>(items, n, c->arena, (uint32_t)c->tma_tile,
                                            (uint32_t)c->tma_stages);
   FC_CUDA(cudaGetLastError());
+  c->n_kernels += 1;
   return FC_OK;
 }
 
@@ -796,6 +807,7 @@ extern "C" int fc_save_async(fc_plan* p, void* host_base, void* compute_stream, 
       uint64_t len = std::min<uint64_t>(kDmaPiece, r.len - o);
       FC_CUDA(cudaMemcpyAsync(hb + r.off + o, c->arena + r.off + o, len, cudaMemcpyDeviceToHost,
                               c->copy_stream));
+      c->n_memcpys += 1;
     }
   FC_CUDA(cudaEventRecord(c->ev_drain_end, c->copy_stream));
   c->save_inflight = true;
@@ -958,6 +970,7 @@ extern "C" int fc_restore_async(fc_plan* p, const void* host_base, void* stream)
       uint64_t len = std::min<uint64_t>(kDmaPiece, r.len - o);
       FC_CUDA(cudaMemcpyAsync(c->arena + r.off + o, hb + r.off + o, len, cudaMemcpyHostToDevice,
                               c->copy_stream));
+      c->n_memcpys += 1;
     }
   FC_CUDA(cudaEventRecord(c->ev_fill_end, c->copy_stream));
   FC_CUDA(cudaStreamWaitEvent(s, c->ev_fill_end, 0));

@@ -112,6 +112,9 @@ int fc_pack_async(fc_plan* plan, void* stream, int variant);
  * (ckpt_saver.py:152-158 + user load_state_dict; fsdp_engine.py:303;
  * megatron_dist_ckpt.py:683). */
 int fc_unpack_async(fc_plan* plan, void* stream, int variant);
+/* how many of this library's kernels / DMA copies the context has enqueued
+ * since creation (bench.py reports the delta over its timed region). */
+int fc_launch_count(fc_ctx* ctx, uint64_t* kernels, uint64_t* memcpys);
 int fc_set_variant(fc_ctx* ctx, int variant);
 /* tuning knobs for the sweep in bench/ncu runs; 0 keeps the current value */
 int fc_set_launch(fc_ctx* ctx, int lsu_ctas_per_sm, int tma_ctas_per_sm,

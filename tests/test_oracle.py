@@ -80,3 +80,20 @@ def test_c_oracle_agrees_with_numpy_oracle(threads):
     rc = lib.oracle_pack(ctypes.c_void_p(dst.ctypes.data), ctypes.c_uint64(n), ptrs, offs, lens,
                          ctypes.c_int(threads))
     assert rc == 0 and np.array_equal(dst, want)
+
+
+@pytest.mark.parametrize("name", list(fixtures.FIXTURES))
+def test_ref_port_matches_golden(name):
+    """The bench's reference arm (oracle/ref_port.py) leaves the same bytes in
+    its segment as the reference did."""
+    from oracle.ref_port import RefPortSaver
+
+    info, image = golden(name)
+    saver = RefPortSaver(f"fc_refport_{os.getpid()}_{name}")
+    try:
+        saver.save({"model_states": fixtures.FIXTURES[name]()})
+        got = np.frombuffer(saver.segment.buf, dtype=np.uint8)
+        assert np.array_equal(got, image)
+        del got
+    finally:
+        saver.close()
