@@ -409,7 +409,9 @@ def measure_stall(ckpt, sd, S, dev, world):
         c = a
         for _ in range(inner):
             c = torch.mm(c, b)
-        return c
+        # like `loss.item()` in a real loop: the host does not run ahead of
+        # the device by more than one step
+        return float(c[0, 0].item())
 
     # size the checkpoint interval so a drain (S over PCIe) always fits in it
     for _ in range(3):
@@ -458,7 +460,8 @@ def measure_stall(ckpt, sd, S, dev, world):
         "checkpoint_every_steps": every,
         "saves_done": [n_a, n_b],
         "saves_attempted": rounds,
-        "method": f"{every * rounds} synthetic steps of {inner} bf16 8192^3 matmuls, a memory "
+        "method": f"{every * rounds} synthetic steps of {inner} bf16 8192^3 matmuls + a "
+                  "loss.item()-style host read per step, a memory "
                   f"checkpoint every {every} steps; stall = (loop wall time - wall time of the "
                   "same loop without checkpoints) / #checkpoints; 'async' = product default "
                   "(returns after enqueueing the gather kernel), 'blocking' = waits for the "

@@ -344,5 +344,8 @@ def get_context(device: int) -> Context:
         ctx = _contexts.get(device)
         if ctx is None or not ctx._h:
             ctx = Context(device)
+            forced = os.getenv("DLROVER_B200_VARIANT", "").lower()
+            if forced in ("lsu", "tma"):  # profiling / A-B runs only
+                ctx.set_variant(VARIANT_LSU if forced == "lsu" else VARIANT_TMA)
             _contexts[device] = ctx
         return ctx
