@@ -128,6 +128,10 @@ class AsyncCheckpointSaver(metaclass=ABCMeta):
         logger.info(f"AsyncSaver({type(self).__name__}) initialized.")
 
     def __del__(self):
+        import sys
+
+        if sys.is_finalizing():
+            return  # the agent exits: segments are left for the next incarnation
         try:
             self.close()
         except Exception:

@@ -115,6 +115,30 @@ def _recv_frame(sock: socket.socket) -> bytes:
     return _recv_exact(sock, size) if size else b""
 
 
+def retry_socket(func):
+    """Decorator: retry `func` once a second while the peer's socket is not
+    there yet (kwarg ``retry``, default 30), then let the error through."""
+
+    def wrapper(self, *args, **kwargs):
+        for _ in range(kwargs.get("retry", 30)):
+            try:
+                return func(self, *args, **kwargs)
+            except (FileNotFoundError, ConnectionRefusedError):
+                time.sleep(1)
+        return func(self, *args, **kwargs)
+
+    return wrapper
+
+
+class LockState(int):
+    """Result of a client-side SharedLock.locked(): truthy iff locked, and also
+    answers `.locked` (the reference hands back the response object there)."""
+
+    @property
+    def locked(self) -> bool:
+        return bool(self)
+
+
 def clear_sock_dir():
     shutil.rmtree(SOCKET_TMP_DIR, ignore_errors=True)
 
@@ -316,8 +340,11 @@ class SharedLock(LocalSocketComm):
         if request.method == "locked":
             return LockedResponse(locked=self.locked())
         if request.method == "release":
-            self.release()
-            held["lock"] = False
+            # only the connection that holds the lock may free it: a stray
+            # second release must not drop a lock someone else has since taken
+            if held["lock"]:
+                self.release()
+                held["lock"] = False
             return SocketResponse()
         raise ValueError(f"unknown lock method {request.method!r}")
 
@@ -350,7 +377,7 @@ class SharedLock(LocalSocketComm):
         if self._lock is not None:
             return self._lock.locked()
         resp = self._request(SocketRequest("locked", self._id, {}))
-        return bool(getattr(resp, "locked", False))
+        return LockState(bool(getattr(resp, "locked", False)))
 
 
 # ------------------------------------------------------------------------- queue --

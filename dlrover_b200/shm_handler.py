@@ -333,6 +333,17 @@ class SharedMemoryHandler:
         self.shared_memory = _create_shared_memory(self._shm_name, create=create, size=size)
         self._need_creation = False
 
+    def _create_tensor_meta(self, value):
+        """Meta of one leaf at the current end of the layout (API parity with
+        the reference's planner hook, ckpt_saver.py:286-301)."""
+        if not torch.is_tensor(value):
+            return value
+        meta = TensorMeta(shape=tuple(value.shape), dtype=value.dtype,
+                          element_size=value.element_size(), numel=value.numel(),
+                          offset=self._buffer_size)
+        self._buffer_size += value.numel() * value.element_size()
+        return meta
+
     # -- pending drain ----------------------------------------------------------------
     def pending_save(self) -> Optional[PendingSave]:
         p = self._pending
