@@ -1,0 +1,484 @@
+"""torch.distributed.checkpoint (DCP) over the checkpoint shared-memory segment.
+
+Contract follows the reference @ 468d632,
+dlrover/trainer/torch/flash_checkpoint/fsdp_engine.py:
+  * SharedMemoryWriter (:158-232): a DCP StorageWriter whose "file" is this
+    rank's shm segment: the items of the local SavePlan are laid out back to
+    back in plan order (:85-107, :133-155), each answered with
+    WriteResult(index, size, _StorageInfo(relative_path="__<rank>_0.distcp",
+    offset, length)); DCP Metadata + non-sharded objects go to the agent's
+    SharedDict under "dcp_metadata" / "no_shard_data" (:225-232, :512-520);
+  * SharedMemoryReader (:235-340) / FileReader (:362-444): read items back from
+    the segment, resp. from "<dir>/__<rank>_0.distcp" + ".metadata" on storage;
+  * FsdpCheckpointEngine (:447-602): every rank is a shard.
+
+Underneath, tensor items are not copied one at a time with blocking
+`shm_tensor.copy_(data)` (:144-147): all CUDA items of the plan become ONE
+descriptor table -> one gather kernel into the HBM arena -> one DMA drain; the
+write results are known at planning time, so DCP's metadata exchange overlaps
+the drain.
+"""
+
+from __future__ import annotations
+
+import dataclasses
+import io
+import os
+import pickle
+from dataclasses import dataclass
+from pathlib import Path
+from typing import Any, Dict, List, Optional, Tuple, Union
+
+import torch
+import torch.distributed as dist
+import torch.distributed.checkpoint as dist_cp
+from torch.distributed.checkpoint.metadata import (
+    STORAGE_TYPES,
+    Metadata,
+    MetadataIndex,
+    TensorStorageMetadata,
+)
+from torch.distributed.checkpoint.planner import (
+    LoadItemType,
+    LoadPlan,
+    LoadPlanner,
+    ReadItem,
+    SavePlan,
+    SavePlanner,
+    WriteItem,
+    WriteItemType,
+)
+from torch.distributed.checkpoint.storage import StorageReader, StorageWriter, WriteResult
+from torch.futures import Future
+
+from ..ckpt_saver import (
+    DLROVER_CKPT_CONFIG_KEY,
+    CheckpointConfig,
+    FsdpDcpSaver,
+    SharedMemoryHandler,
+)
+from ..common import env_utils
+from ..common.constants import CheckpointConstant
+from ..common.log import default_logger as logger
+from .engine import (
+    CheckpointEngine,
+    check_all_rank_ready,
+    timer,
+    verify_all_rank_step_consistent,
+)
+
+try:  # moved around between torch releases
+    from torch.distributed.checkpoint.filesystem import DEFAULT_SUFFIX
+except ImportError:  # pragma: no cover
+    DEFAULT_SUFFIX = ".distcp"
+from torch.distributed._shard._utils import narrow_tensor_by_index
+
+
+@dataclass
+class _StorageInfo:
+    """Where one item lives: file (segment) name, byte offset, byte length."""
+
+    relative_path: str
+    offset: int
+    length: int
+
+
+@dataclass
+class _StoragePrefix:
+    prefix: str
+
+
+def _tensor_item_size(item: WriteItem) -> int:
+    assert item.tensor_data is not None
+    numel = 1
+    for s in item.tensor_data.size:
+        numel *= s
+    return numel * torch._utils._element_size(item.tensor_data.properties.dtype)
+
+
+def _get_buffer_size(files: List[Tuple[str, WriteItem]], planner: SavePlanner) -> int:
+    """Bytes needed for all items: tensors by metadata, BYTE_IO by content."""
+    total = 0
+    for _, item in files:
+        if item.type != WriteItemType.BYTE_IO:
+            total += _tensor_item_size(item)
+        else:
+            total += planner.resolve_data(item).getbuffer().nbytes
+    return total
+
+
+def _stage_items(files: List[Tuple[str, WriteItem]], planner: SavePlanner):
+    """Resolve every item once and lay the plan out back to back.
+
+    Returns (write_results, no_shard_data, device_ranges, host_ranges,
+    raw_chunks, total_bytes).  Non-SHARD items are also collected in
+    `no_shard_data` (only rank 0 plans them; they are broadcast so any rank can
+    restore from memory)."""
+    results: List[WriteResult] = []
+    no_shard: Dict[str, STORAGE_TYPES] = {}
+    device_ranges, host_ranges, raw_chunks = [], [], []
+    offset = 0
+    for storage_key, item in files:
+        data = planner.resolve_data(item)
+        if torch.is_tensor(data):
+            data = data.detach()
+        if item.type != WriteItemType.SHARD:
+            no_shard[item.index.fqn] = data
+        if item.type == WriteItemType.BYTE_IO:
+            assert isinstance(data, io.BytesIO)
+            buf = data.getbuffer()
+            length = buf.nbytes
+            raw_chunks.append((buf, offset))
+        else:
+            assert isinstance(data, torch.Tensor)
+            length = data.numel() * data.element_size()
+            if length:
+                (device_ranges if data.is_cuda else host_ranges).append((data, offset, length))
+        results.append(WriteResult(index=item.index, size_in_bytes=length,
+                                   storage_data=_StorageInfo(storage_key, offset, length)))
+        offset += length
+    return results, no_shard, device_ranges, host_ranges, raw_chunks, offset
+
+
+def _write_memory_from_list(shm_handler: SharedMemoryHandler,
+                            files: List[Tuple[str, WriteItem]], planner: SavePlanner,
+                            blocking: bool = True):
+    """Write all items of `files` into the handler's segment (sized on demand).
+    Returns (write_results, no_shard_data, pending)."""
+    results, no_shard, dev, host, raw, total = _stage_items(files, planner)
+    if total > 0:
+        shm_handler.ensure_segment(total)
+    pending = None
+    if total > 0:
+        pending = shm_handler.write_ranges(dev, host, raw, blocking=blocking,
+                                           keepalive=[d for d, _, _ in dev])
+    return results, no_shard, pending
+
+
+class SharedMemoryWriter(StorageWriter):
+    """DCP StorageWriter whose storage is the shared-memory segment."""
+
+    def __init__(self, shm_handler: SharedMemoryHandler, blocking: bool = True) -> None:
+        super().__init__()
+        self.file_name = ""
+        self.shm_handler = shm_handler
+        self.metadata: Dict[str, Any] = {}
+        self.blocking = blocking
+        self.pending = None
+
+    def reset(self, checkpoint_id: Union[str, os.PathLike, None] = None) -> None:
+        pass
+
+    @classmethod
+    def validate_checkpoint_id(cls, checkpoint_id: Union[str, os.PathLike]) -> bool:
+        return True
+
+    def set_up_storage_writer(self, is_coordinator: bool, *args, **kwargs) -> None:
+        pass
+
+    def prepare_local_plan(self, plan: SavePlan) -> SavePlan:
+        return plan
+
+    def prepare_global_plan(self, global_plan: List[SavePlan]) -> List[SavePlan]:
+        return [dataclasses.replace(plan, storage_data=_StoragePrefix(f"__{i}_"))
+                for i, plan in enumerate(global_plan)]
+
+    def write_data(self, plan: SavePlan, planner: SavePlanner) -> Future[List[WriteResult]]:
+        prefix: _StoragePrefix = plan.storage_data
+        self.file_name = f"{prefix.prefix}0{DEFAULT_SUFFIX}"
+        files = [(self.file_name, item) for item in plan.items]
+        results, no_shard, self.pending = _write_memory_from_list(
+            self.shm_handler, files, planner, blocking=self.blocking)
+        self.metadata["no_shard_data"] = no_shard
+        fut: Future[List[WriteResult]] = Future()
+        fut.set_result(results)
+        return fut
+
+    def finish(self, metadata: Metadata, results: List[List[WriteResult]]) -> None:
+        storage_md = {}
+        for per_rank in results:
+            storage_md.update({wr.index: wr.storage_data for wr in per_rank})
+        metadata.storage_data = storage_md
+        self.metadata["dcp_metadata"] = metadata
+
+
+def _load_item(read_item: ReadItem, item_bytes: io.BytesIO, planner: LoadPlanner,
+               tensor_md: Optional[TensorStorageMetadata], pickled: bool = False):
+    """Hand one stored item to the planner (bytes) or copy it into the
+    planner's destination tensor (narrowed to the requested slice)."""
+    if read_item.type == LoadItemType.BYTE_IO:
+        planner.load_bytes(read_item, item_bytes)
+        return
+    if pickled:
+        tensor = torch.load(item_bytes)
+    else:
+        assert tensor_md is not None
+        flat = torch.frombuffer(item_bytes.getbuffer(), dtype=tensor_md.properties.dtype)
+        tensor = flat.reshape(_chunk_shape(tensor_md, read_item))
+    tensor = narrow_tensor_by_index(tensor, read_item.storage_offsets, read_item.lengths)
+    target = planner.resolve_tensor(read_item).detach()
+    assert target.size() == tensor.size(), (
+        f"req {read_item.storage_index} mismatch sizes {target.size()} vs {tensor.size()}")
+    target.copy_(tensor)
+    planner.commit_tensor(read_item, target)
+
+
+def _chunk_shape(md: TensorStorageMetadata, read_item: ReadItem):
+    """Shape of the STORED chunk the item points at (the request may be a
+    sub-box of it when the world was resharded); falls back to the requested
+    lengths, which is what the reference always assumes (:293-296)."""
+    where = read_item.storage_index.offset
+    chunks = getattr(md, "chunks", None) or []
+    if where is not None:
+        for c in chunks:
+            if tuple(c.offsets) == tuple(where):
+                return tuple(c.sizes)
+    if len(chunks) == 1:
+        return tuple(chunks[0].sizes)
+    return tuple(read_item.lengths)
+
+
+class SharedMemoryReader(StorageReader):
+    """DCP StorageReader over the shared-memory segment."""
+
+    def __init__(self, shm_handler: SharedMemoryHandler) -> None:
+        super().__init__()
+        self.storage_data: Dict[MetadataIndex, _StorageInfo] = {}
+        self.shm_handler = shm_handler
+        self.state_dict_metadata: Dict[str, STORAGE_TYPES] = {}
+        self.no_shard_data: Dict[str, STORAGE_TYPES] = {}
+
+    def read_data(self, plan: LoadPlan, planner: LoadPlanner) -> Future[None]:
+        self.shm_handler.wait_pending()
+        if self.shm_handler.shared_memory is None:
+            self.shm_handler.init_shared_memory()
+        for read_item in plan.items:
+            info = self.storage_data[read_item.storage_index]
+            pickled = False
+            if not read_item.storage_index.offset:
+                # non-sharded entry: taken from the broadcast copy, not the segment
+                data = self.no_shard_data[read_item.storage_index.fqn]
+                if isinstance(data, io.BytesIO):
+                    item_bytes = data
+                else:
+                    item_bytes = io.BytesIO()
+                    torch.save(data, item_bytes)
+                pickled = True
+            else:
+                assert self.shm_handler.shared_memory is not None
+                item_bytes = io.BytesIO(
+                    self.shm_handler.shared_memory.buf[info.offset:info.offset + info.length])
+            item_bytes.seek(0)
+            md = None
+            if read_item.type != LoadItemType.BYTE_IO:
+                md = self.state_dict_metadata[read_item.storage_index.fqn]
+            _load_item(read_item, item_bytes, planner, md, pickled=pickled)
+        fut: Future = Future()
+        fut.set_result(None)
+        return fut
+
+    def read_metadata(self, *args, **kwargs) -> Metadata:
+        cached = self.shm_handler.metadata.get()
+        self.no_shard_data = cached["no_shard_data"]
+        return cached["dcp_metadata"]
+
+    def set_up_storage_reader(self, metadata: Metadata, is_coordinator: bool, *args,
+                              **kwargs) -> None:
+        self.storage_data = metadata.storage_data
+        self.state_dict_metadata = metadata.state_dict_metadata
+        assert self.storage_data is not None
+
+    def prepare_local_plan(self, plan: LoadPlan) -> LoadPlan:
+        return plan
+
+    def prepare_global_plan(self, global_plan: List[LoadPlan]) -> List[LoadPlan]:
+        return global_plan
+
+    def reset(self, checkpoint_id: Union[str, os.PathLike, None] = None) -> None:
+        pass
+
+    @classmethod
+    def validate_checkpoint_id(cls, checkpoint_id: Union[str, os.PathLike]) -> bool:
+        return True
+
+
+class FileReader(StorageReader):
+    """DCP StorageReader over the files the agent wrote from the segments
+    ("__<rank>_0.distcp" raw bytes + pickled ".metadata")."""
+
+    def __init__(self, path: Union[str, os.PathLike]) -> None:
+        super().__init__()
+        self.path = Path(path)
+        self.storage_data: Dict[MetadataIndex, _StorageInfo] = {}
+        self.state_dict_metadata: Dict[str, STORAGE_TYPES] = {}
+
+    def read_data(self, plan: LoadPlan, planner: LoadPlanner) -> Future[None]:
+        by_file: Dict[str, List[ReadItem]] = {}
+        for item in plan.items:
+            by_file.setdefault(self.storage_data[item.storage_index].relative_path,
+                               []).append(item)
+        for relative_path, items in by_file.items():
+            with (self.path / relative_path).open("rb") as f:
+                for item in items:
+                    info = self.storage_data[item.storage_index]
+                    f.seek(info.offset)
+                    item_bytes = io.BytesIO(f.read(info.length))
+                    md = None
+                    if item.type != LoadItemType.BYTE_IO:
+                        md = self.state_dict_metadata[item.storage_index.fqn]
+                    _load_item(item, item_bytes, planner, md)
+        fut: Future = Future()
+        fut.set_result(None)
+        return fut
+
+    def read_metadata(self, *args, **kwargs) -> Metadata:
+        with (self.path / ".metadata").open("rb") as f:
+            return pickle.load(f)
+
+    def set_up_storage_reader(self, metadata: Metadata, is_coordinator: bool, *args,
+                              **kwargs) -> None:
+        self.storage_data = metadata.storage_data
+        self.state_dict_metadata = metadata.state_dict_metadata
+        assert self.storage_data is not None
+
+    def prepare_local_plan(self, plan: LoadPlan) -> LoadPlan:
+        return plan
+
+    def prepare_global_plan(self, global_plan: List[LoadPlan]) -> List[LoadPlan]:
+        return global_plan
+
+    def reset(self, checkpoint_id: Union[str, os.PathLike, None] = None) -> None:
+        pass
+
+    @classmethod
+    def validate_checkpoint_id(cls, checkpoint_id: Union[str, os.PathLike]) -> bool:
+        return True
+
+
+def _dcp_save(state_dict, writer):
+    if hasattr(dist_cp, "save"):
+        return dist_cp.save(state_dict, storage_writer=writer)
+    return dist_cp.save_state_dict(state_dict=state_dict, storage_writer=writer)
+
+
+class FsdpCheckpointEngine(CheckpointEngine):
+    """Sharded FSDP state through DCP: every rank writes its local shards to its
+    own segment; the agent dumps each segment as "__<rank>_0.distcp"."""
+
+    def __init__(self, checkpoint_dir: str, storage, comm_backend="",
+                 save_timeout=CheckpointConstant.SAVE_TIMEOUT, async_drain=None):
+        super().__init__(checkpoint_dir, storage, comm_backend, save_timeout,
+                         async_drain=async_drain)
+        self._shm_writer = SharedMemoryWriter(shm_handler=self._shm_handler,
+                                              blocking=not self._async_drain)
+        self._shm_reader = SharedMemoryReader(self._shm_handler)
+
+    def get_saving_ranks(self):
+        return None  # every rank holds a shard
+
+    @timer
+    def save_to_memory(self, step, state_dict, paths: Dict[str, str]):
+        """`paths["model_states"]` is the DIRECTORY of the step; the agent
+        stores this rank's segment there as "__<rank>_0.distcp"."""
+        if self._local_rank != self.local_shard_id:
+            return False
+        pending = self._shm_handler.pending_save()
+        acquired = False if pending is not None else self._shm_lock.acquire(blocking=False)
+        all_rank_ready = check_all_rank_ready(self._saver_group, acquired)
+        if not all_rank_ready:
+            logger.info(f"Rank {self._rank} skips the save the checkpoint in CPU memory since "
+                        "it is saving the latest checkpoint from the CPU memory into the "
+                        "storage.")
+            if acquired:
+                self._shm_lock.release()
+            return False
+
+        conf = CheckpointConfig(rank=self._rank, group_rank=self._group_rank,
+                                world_size=self._world_size, step=step)
+        conf.writing_shm = True
+        try:
+            _dcp_save(state_dict, self._shm_writer)
+            # rank 0's DCP metadata and non-sharded objects go to every rank so
+            # each of them can restore from its own memory
+            shared = [self._shm_writer.metadata]
+            if dist.is_initialized():
+                dist.broadcast_object_list(shared, src=0)
+            self._shm_writer.metadata = shared[0]
+            name = CheckpointConstant.MODEL_STATES_NAME
+            conf.paths = {name: os.path.join(paths[name], self._shm_writer.file_name)}
+            meta_dict = {DLROVER_CKPT_CONFIG_KEY: conf}
+            meta_dict.update(self._shm_writer.metadata)
+            self._shm_handler.metadata.set(meta_dict)  # step visible, bytes not yet final
+        except BaseException:
+            if acquired:
+                self._shm_handler.wait_pending()
+                self._shm_lock.release()
+            raise
+
+        def completed():
+            conf.writing_shm = False
+            self._shm_handler.metadata.set(meta_dict)
+            if acquired:
+                self._shm_lock.release()
+
+        drain = self._shm_writer.pending
+        if drain is None or drain.done():
+            if drain is not None:
+                drain.wait()
+            completed()
+        else:
+            import threading
+
+            def waiter():
+                try:
+                    drain.wait()
+                finally:
+                    completed()
+
+            threading.Thread(target=waiter, name="fc-fsdp-drain", daemon=True).start()
+            self._finalizer = waiter
+        self._cached_step = conf.step
+        return True
+
+    def save_to_storage(self, step, state_dict, paths: Dict[str, str]):
+        success = True
+        if step > self._cached_step:
+            success = self.save_to_memory(step, state_dict, paths)
+        if dist.is_initialized():
+            dist.barrier()
+        if self._local_rank == 0 and success:
+            logger.info("Put a save event to notify the agent persists checkpoint.")
+            self._notify_save_event(step)
+        if success:
+            self.latest_step = step
+
+    def get_saver_class(self):
+        return FsdpDcpSaver
+
+    def get_local_shard_num(self):
+        return env_utils.get_local_world_size()
+
+    def get_global_shard_num(self):
+        return dist.get_world_size() if dist.is_initialized() else 1
+
+    def load(self, resume_path=""):
+        """A StorageReader: over shared memory when every rank holds the same
+        step there, else over the files at `resume_path` / the tracked step;
+        None when there is nothing to read."""
+        self._shm_handler.wait_pending()
+        config = self._shm_handler.get_checkpoint_config(CheckpointConfig())
+        passed = verify_all_rank_step_consistent(self._saver_group, config.step)
+        if passed and not self._shm_handler.no_checkpoint_state():
+            logger.info(f"Create a shared memory reader with step {config.step}.")
+            return self._shm_reader
+        if not resume_path:
+            resume_path = self._get_track_resume_path()
+        if resume_path and os.path.exists(resume_path):
+            logger.info(f"Create a storage reader with path {resume_path}.")
+            return FileReader(resume_path)
+        return None
+
+    def _get_track_resume_path(self):
+        tracker = os.path.join(self.checkpoint_dir, CheckpointConstant.TRACER_FILE_NAME)
+        step = self.storage.read(tracker)
+        return os.path.join(self.checkpoint_dir, step) if step else ""

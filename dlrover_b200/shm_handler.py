@@ -208,17 +208,18 @@ class _DeviceStager:
                 logger.warning(f"host_unregister: {e}")
             self._registered_addr = 0
 
-    def plan_for(self, leaves: List[Tuple[torch.Tensor, TensorMeta]], keepalive: list):
+    def plan_for(self, ranges: List[Tuple[torch.Tensor, int, int]], keepalive: list):
+        """ranges: (tensor, segment offset, nbytes) per device-resident leaf."""
         ptrs, offs, lens = [], [], []
-        for t, m in leaves:
+        for t, off, nbytes in ranges:
             if not t.is_contiguous():
                 # rare (state_dict tensors are contiguous); device-side repack,
                 # kept alive until the pack kernel has consumed it
                 t = t.contiguous()
                 keepalive.append(t)
             ptrs.append(t.data_ptr())
-            offs.append(m.offset)
-            lens.append(m.numel * m.element_size)
+            offs.append(off)
+            lens.append(nbytes)
         key = (tuple(ptrs), tuple(offs), tuple(lens))
         for i, p in enumerate(self._plans):
             if p.key == key:
@@ -356,22 +357,10 @@ class SharedMemoryHandler:
         return p.wait(timeout)
 
     # -- save ---------------------------------------------------------------------------
-    def _ensure_segment(self, lay: _Layout):
-        if self.shared_memory is not None and self.shared_memory.size == lay.total \
-                and not self._need_creation:
-            return
-        if self._stager is not None:
-            self._stager.detach()
-        if self.shared_memory is not None:
-            self.shared_memory.close()
-            self.shared_memory = None
-        self.init_shared_memory(create=True, size=lay.total)
-        self._buffer_size = lay.total
-
-    def _stager_for(self, leaves) -> _DeviceStager:
-        dev = leaves[0][0].device
+    def _stager_for(self, tensors) -> _DeviceStager:
+        dev = tensors[0].device
         index = dev.index if dev.index is not None else torch.cuda.current_device()
-        for t, _ in leaves:
+        for t in tensors:
             if t.device != dev:
                 raise ValueError(
                     "all CUDA tensors of one checkpoint shard must live on one device; "
@@ -381,6 +370,67 @@ class SharedMemoryHandler:
                 self._stager.close()
             self._stager = _DeviceStager(index)
         return self._stager
+
+    def ensure_segment(self, total: int):
+        """Map a segment of exactly `total` bytes (re-creating it on a size
+        change)."""
+        if self.shared_memory is not None and self.shared_memory.size == total \
+                and not self._need_creation:
+            return
+        if self._stager is not None:
+            self._stager.detach()
+        if self.shared_memory is not None:
+            self.shared_memory.close()
+            self.shared_memory = None
+        self.init_shared_memory(create=True, size=total)
+        self._buffer_size = total
+
+    def write_ranges(self, device_ranges, host_ranges, raw_chunks=(), *, blocking=True,
+                     stream=None, finish: Optional[Callable[[], None]] = None,
+                     keepalive: Optional[list] = None):
+        """Move bytes into the (already sized) segment.
+
+        device_ranges / host_ranges: (tensor, segment offset, nbytes) for CUDA /
+        CPU tensors; raw_chunks: (bytes-like, offset).  CUDA ranges go through
+        one gather kernel + DMA drain, the rest is written by the host right
+        away.  `finish` runs once everything has landed — inline when blocking,
+        else on the completion thread of the returned PendingSave.
+        """
+        keepalive = keepalive if keepalive is not None else []
+        for chunk, off in raw_chunks:
+            view = memoryview(chunk).cast("B")
+            self.shared_memory.buf[off:off + view.nbytes] = view
+        if host_ranges:
+            keep, ptrs, offs, lens = [], [], [], []
+            for t, off, nbytes in host_ranges:
+                c = t.detach()
+                if not c.is_contiguous():
+                    c = c.contiguous()
+                keep.append(c)
+                ptrs.append(c.data_ptr())
+                offs.append(off)
+                lens.append(nbytes)
+            native.host_pack(self.shared_memory.address, ptrs, offs, lens, _host_threads())
+            del keep
+        ctx, ticket = None, 0
+        if device_ranges:
+            stager = self._stager_for([r[0] for r in device_ranges])
+            stager.attach(self.shared_memory)
+            plan = stager.plan_for(device_ranges, keepalive)
+            if stream is None:
+                stream = torch.cuda.current_stream(stager.device_index)
+            ticket = plan.save_async(self.shared_memory.address, stream)
+            ctx = stager.ctx
+        pending = PendingSave(ctx, ticket, finish or (lambda: None), keepalive)
+        self._pending = pending
+        if blocking or ctx is None:
+            pending._complete()
+            self.last_timings = pending.timings
+            pending.wait()  # re-raise a drain error
+            return None
+        threading.Thread(target=self._run_completion, args=(pending,), name="fc-drain",
+                         daemon=True).start()
+        return pending
 
     def save_state_dict(self, state_dict, blocking: bool = True, stream=None,
                         on_complete: Optional[Callable[[], None]] = None):
@@ -394,11 +444,8 @@ class SharedMemoryHandler:
         """
         self.wait_pending()
         lay = plan_layout(state_dict)
-        if lay.total == 0 and self.shared_memory is None:
-            # nothing but non-tensor leaves: still publish the meta tree
-            lay.total = 0
         if lay.total > 0:
-            self._ensure_segment(lay)
+            self.ensure_segment(lay.total)
         self._signature = lay.signature
         meta_dict = lay.meta
         conf: CheckpointConfig = meta_dict[DLROVER_CKPT_CONFIG_KEY]
@@ -406,21 +453,6 @@ class SharedMemoryHandler:
         report_local_event(EventReportConstants.TYPE_INFO, str(conf.rank),
                            EventReportConstants.ACTION_MEM_CKPT_START, f"step={conf.step}")
         self.metadata.set(meta_dict)
-
-        if lay.host_leaves:
-            assert self.shared_memory is not None
-            keep = []
-            ptrs, offs, lens = [], [], []
-            for t, m in lay.host_leaves:
-                c = t.detach()
-                if not c.is_contiguous():
-                    c = c.contiguous()
-                keep.append(c)
-                ptrs.append(c.data_ptr())
-                offs.append(m.offset)
-                lens.append(m.numel * m.element_size)
-            native.host_pack(self.shared_memory.address, ptrs, offs, lens, _host_threads())
-            del keep
 
         def finish():
             conf.writing_shm = False
@@ -431,29 +463,14 @@ class SharedMemoryHandler:
             if on_complete is not None:
                 on_complete()
 
-        keepalive: list = []
-        ctx, ticket = None, 0
-        if lay.device_leaves:
-            assert self.shared_memory is not None
-            stager = self._stager_for(lay.device_leaves)
-            stager.attach(self.shared_memory)
-            plan = stager.plan_for(lay.device_leaves, keepalive)
-            if stream is None:
-                stream = torch.cuda.current_stream(stager.device_index)
-            ticket = plan.save_async(self.shared_memory.address, stream)
-            ctx = stager.ctx
-            keepalive.append(state_dict)  # tensors must outlive the gather kernel
+        def triples(leaves):
+            return [(t, m.offset, m.numel * m.element_size) for t, m in leaves]
 
-        pending = PendingSave(ctx, ticket, finish, keepalive)
-        self._pending = pending
-        if blocking or ctx is None:
-            pending._complete()
-            self.last_timings = pending.timings
-            pending.wait()  # re-raise a drain error
-            return None
-        threading.Thread(target=self._run_completion, args=(pending,), name="fc-drain",
-                         daemon=True).start()
-        return pending
+        # the tensors must outlive the gather kernel
+        keepalive = [state_dict] if lay.device_leaves else []
+        return self.write_ranges(triples(lay.device_leaves), triples(lay.host_leaves),
+                                 blocking=blocking, stream=stream, finish=finish,
+                                 keepalive=keepalive)
 
     def _run_completion(self, pending: PendingSave):
         pending._complete()
@@ -545,9 +562,10 @@ class SharedMemoryHandler:
                 for t, _ in device_pairs:
                     if not t.is_contiguous():
                         raise ValueError("restore_into needs contiguous CUDA targets")
-                stager = self._stager_for(device_pairs)
+                stager = self._stager_for([t for t, _ in device_pairs])
                 stager.attach(self.shared_memory)
-                plan = stager.plan_for(device_pairs, [])
+                plan = stager.plan_for(
+                    [(t, m.offset, m.numel * m.element_size) for t, m in device_pairs], [])
                 if stream is None:
                     stream = torch.cuda.current_stream(stager.device_index)
                 plan.restore_async(self.shared_memory.address, stream)
