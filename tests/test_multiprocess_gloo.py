@@ -1,0 +1,109 @@
+"""world_size=2 over gloo on CPU: the N>1 host logic — saving-rank policy,
+readiness collective, per-rank segments, barrier + SAVE event, done-file commit
+with global_shard_num=2, step-consistency check on load
+(reference: checkpoint_egine_test.py:63-76,331-342 uses mp.spawn the same way)."""
+
+import os
+import sys
+import tempfile
+import time
+import uuid
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, run_id, ckpt_dir, mode, out_dir):
+    sys.path.insert(0, ROOT)
+    os.environ.update({
+        "RANK": str(rank), "LOCAL_RANK": str(rank), "WORLD_SIZE": str(world),
+        "LOCAL_WORLD_SIZE": str(world), "GROUP_WORLD_SIZE": "1", "GROUP_RANK": "0",
+        "MASTER_ADDR": "127.0.0.1", "MASTER_PORT": str(port), "TORCHELASTIC_RUN_ID": run_id,
+        "DLROVER_LOG_LEVEL": "WARNING",
+    })
+    os.environ.pop("ROLE_NAME", None)  # local rank 0 forks the saver daemon
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from dlrover_b200.common.constants import CheckpointConstant
+    from dlrover_b200.common.storage import PosixDiskStorage
+    from dlrover_b200.flash_checkpoint.api import DdpCheckpointer, StorageType
+    from dlrover_b200.flash_checkpoint.engine import check_all_rank_ready
+
+    result = {}
+    try:
+        if mode == "sharded":
+            ckpt = DdpCheckpointer(ckpt_dir, local_shard_num=world, global_shard_num=world)
+            eng = ckpt.engine
+            result["saving_ranks"] = eng._saving_ranks
+            result["shard_id"] = eng.local_shard_id
+            sd = {"w": torch.full((1000,), float(rank + 1)), "rank": rank}
+            ckpt.save_checkpoint(3, sd, storage_type=StorageType.MEMORY)
+            back = ckpt.load_checkpoint()
+            result["mem_ok"] = bool(torch.equal(back["w"], sd["w"]) and back["rank"] == rank)
+            del back
+            ckpt.save_checkpoint(4, sd, storage_type=StorageType.DISK)
+            ckpt.wait_latest_checkpoint(timeout=90)
+            result["tracker"] = open(os.path.join(ckpt_dir, "dlrover_latest.txt")).read()
+            result["files"] = sorted(os.listdir(os.path.join(ckpt_dir, "4")))
+            mine = torch.load(os.path.join(ckpt_dir, "4", f"rank_{rank}.pt"))
+            result["disk_ok"] = bool(torch.equal(mine["w"], sd["w"]))
+            result["ready_all"] = bool(check_all_rank_ready(None, True))
+            result["ready_one_not"] = bool(check_all_rank_ready(None, rank != 1))
+        else:  # replicated: only local rank 0 writes
+            ckpt = DdpCheckpointer(ckpt_dir)
+            eng = ckpt.engine
+            result["saving_ranks"] = eng._saving_ranks
+            sd = {"w": torch.arange(100, dtype=torch.float32)}
+            ckpt.save_checkpoint(7, sd, storage_type=StorageType.DISK)
+            result["cached_step"] = eng._cached_step
+            ckpt.wait_latest_checkpoint(timeout=90)
+            result["files"] = sorted(os.listdir(os.path.join(ckpt_dir, "7")))
+            # rank 1 never wrote memory: steps differ across ranks, so nobody
+            # restores from memory and both fall back to rank 0's file
+            loaded = ckpt.load_checkpoint()
+            result["load_ok"] = bool(torch.equal(loaded["w"], sd["w"]))
+        dist.barrier()
+        eng.close()
+    finally:
+        torch.save(result, os.path.join(out_dir, f"r{rank}.pt"))
+        dist.destroy_process_group()
+
+
+def _run(mode):
+    world = 2
+    run_id = "mp" + uuid.uuid4().hex[:8]
+    port = 29600 + (os.getpid() * 7 + hash(mode)) % 1500
+    with tempfile.TemporaryDirectory() as ckpt_dir, tempfile.TemporaryDirectory() as out_dir:
+        mp.spawn(_worker, args=(world, port, run_id, ckpt_dir, mode, out_dir), nprocs=world,
+                 join=True)
+        results = [torch.load(os.path.join(out_dir, f"r{r}.pt")) for r in range(world)]
+    import glob
+    import shutil
+    shutil.rmtree(os.path.join("/tmp/ckpt_sock", run_id), ignore_errors=True)
+    for f in glob.glob(f"/dev/shm/{run_id}_*"):
+        os.unlink(f)
+    return results
+
+
+@pytest.mark.timeout(300)
+def test_every_rank_is_a_shard():
+    r0, r1 = _run("sharded")
+    for r, res in enumerate((r0, r1)):
+        assert res["saving_ranks"] == [0, 1]
+        assert res["shard_id"] == r
+        assert res["mem_ok"] and res["disk_ok"]
+        assert res["tracker"] == "4"
+        assert res["files"] == ["rank_0.pt", "rank_1.pt"]
+        assert res["ready_all"] is True and res["ready_one_not"] is False
+
+
+@pytest.mark.timeout(300)
+def test_replicated_state_only_local_rank0_saves():
+    r0, r1 = _run("replicated")
+    assert r0["saving_ranks"] == [0] and r1["saving_ranks"] == [0]
+    assert r0["cached_step"] == 7 and r1["cached_step"] == -1
+    assert r0["files"] == ["rank_0.pt"] and r1["files"] == ["rank_0.pt"]
+    assert r0["load_ok"] and r1["load_ok"]
