@@ -64,6 +64,7 @@ _SIGNATURES = {
     "fc_save_poll": (ctypes.c_int, [_vp, _u64]),
     "fc_save_wait": (ctypes.c_int, [_vp, _u64]),
     "fc_save_timings": (ctypes.c_int, [_vp, _u64, _fp, _fp, _fp]),
+    "fc_set_drain": (ctypes.c_int, [_vp, _u64, ctypes.c_int]),
     "fc_host_pack": (
         ctypes.c_int,
         [_vp, _u32, ctypes.POINTER(_vp), ctypes.POINTER(_u64), ctypes.POINTER(_u64), ctypes.c_int],
@@ -275,6 +276,10 @@ class Context:
                                          tma_stages, tma_tile_bytes),
             "fc_set_launch",
         )
+
+    def set_drain(self, piece_bytes: int = 0, depth: int = 0):
+        _check(load_library().fc_set_drain(self.handle, int(piece_bytes), int(depth)),
+               "fc_set_drain")
 
     # -- save / restore tickets ---------------------------------------------------
     def save_pack_done(self, ticket: int) -> bool:

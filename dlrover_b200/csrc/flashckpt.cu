@@ -36,7 +36,12 @@
 #include <unistd.h>
 
 #include <algorithm>
+#include <condition_variable>
+#include <deque>
+#include <mutex>
 #include <new>
+#include <string>
+#include <thread>
 #include <vector>
 
 // ------------------------------------------------------------------ errors --
@@ -91,7 +96,15 @@ struct FcRun {  // merged contiguous arena range (drain/fill DMA granularity)
 constexpr int kLsuThreads = 256;
 constexpr int kLsuUnroll = 4;
 constexpr uint32_t kDefaultChunk = 256u << 10;      // work-item size
-constexpr uint64_t kDmaPiece = 256ull << 20;        // drain/fill memcpy size
+constexpr uint64_t kDmaPiece = 256ull << 20;        // restore fill memcpy size
+// Drain pacing: the D2H copy engine serves copies in submission order across
+// streams, so a drain submitted as one batch delays every unrelated D2H copy
+// of the process (a `loss.item()`!) until the whole checkpoint has left the
+// device.  The pump thread therefore keeps only kDrainDepth pieces of
+// kDrainPiece bytes in flight: a foreign copy waits for <= ~1 ms of drain.
+constexpr uint64_t kDrainPiece = 32ull << 20;
+constexpr int kDrainDepth = 2;
+constexpr int kDrainRing = 8;
 
 // ------------------------------------------------------------ device helpers --
 
@@ -375,7 +388,67 @@ struct fc_ctx {
   std::vector<void*> registered;
   // evidence counters: kernels launched / DMA copies enqueued by this context
   uint64_t n_kernels = 0, n_memcpys = 0;
+  // drain pump (one thread per context, started lazily)
+  std::thread pump;
+  std::mutex mu;
+  std::condition_variable cv;
+  struct DrainJob {
+    uint8_t* host = nullptr;
+    std::vector<FcRun> runs;
+    uint64_t ticket = 0;
+  };
+  std::deque<DrainJob> jobs;
+  bool pump_stop = false;
+  uint64_t drained_ticket = 0;  // last ticket whose bytes are all in host memory
+  int drain_rc = FC_OK;         // sticky error of the pump
+  std::string drain_err;
+  cudaEvent_t ring[kDrainRing] = {};
+  uint64_t drain_piece = kDrainPiece;
+  int drain_depth = kDrainDepth;
 };
+
+static void pump_main(fc_ctx* c) {
+  cudaSetDevice(c->device);
+  for (;;) {
+    fc_ctx::DrainJob job;
+    {
+      std::unique_lock<std::mutex> lk(c->mu);
+      c->cv.wait(lk, [&] { return c->pump_stop || !c->jobs.empty(); });
+      if (c->jobs.empty()) return;  // stop requested and nothing queued
+      job = std::move(c->jobs.front());
+      c->jobs.pop_front();
+    }
+    cudaError_t e = cudaStreamWaitEvent(c->copy_stream, c->ev_pack_end, 0);
+    if (e == cudaSuccess) e = cudaEventRecord(c->ev_drain_start, c->copy_stream);
+    const int depth = std::max(1, std::min(c->drain_depth, kDrainRing));
+    uint64_t k = 0, copies = 0;
+    for (const FcRun& r : job.runs) {
+      for (uint64_t o = 0; o < r.len && e == cudaSuccess; o += c->drain_piece) {
+        const uint64_t len = std::min<uint64_t>(c->drain_piece, r.len - o);
+        if (k >= (uint64_t)depth) e = cudaEventSynchronize(c->ring[k % depth]);  // piece k-depth
+        if (e == cudaSuccess)
+          e = cudaMemcpyAsync(job.host + r.off + o, c->arena + r.off + o, len,
+                              cudaMemcpyDeviceToHost, c->copy_stream);
+        if (e == cudaSuccess) e = cudaEventRecord(c->ring[k % depth], c->copy_stream);
+        ++k;
+        ++copies;
+      }
+    }
+    if (e == cudaSuccess) e = cudaEventRecord(c->ev_drain_end, c->copy_stream);
+    if (e == cudaSuccess) e = cudaEventSynchronize(c->ev_drain_end);
+    {
+      std::lock_guard<std::mutex> lk(c->mu);
+      c->n_memcpys += copies;
+      if (e != cudaSuccess) {
+        c->drain_rc = FC_ECUDA;
+        c->drain_err = std::string("drain pump: ") + cudaGetErrorString(e);
+        (void)cudaGetLastError();
+      }
+      c->drained_ticket = job.ticket;
+    }
+    c->cv.notify_all();
+  }
+}
 
 struct fc_plan {
   fc_ctx* ctx = nullptr;
@@ -428,6 +501,9 @@ extern "C" int fc_ctx_create(int device, fc_ctx** out) {
                         &c->ev_fill_start, &c->ev_fill_end,  &c->ev_scatter_end};
   for (cudaEvent_t* ev : evs)
     if (e == cudaSuccess) e = cudaEventCreate(ev);
+  for (int i = 0; i < kDrainRing; ++i)
+    if (e == cudaSuccess)
+      e = cudaEventCreateWithFlags(&c->ring[i], cudaEventDisableTiming | cudaEventBlockingSync);
   if (e != cudaSuccess) {
     fc_ctx_destroy(c);
     return fail(FC_ECUDA, "fc_ctx_create: %s", cudaGetErrorString(e));
@@ -439,7 +515,17 @@ extern "C" int fc_ctx_create(int device, fc_ctx** out) {
 extern "C" int fc_ctx_destroy(fc_ctx* c) {
   if (!c) return FC_OK;
   DeviceGuard g(c->device);
+  if (c->pump.joinable()) {
+    {
+      std::lock_guard<std::mutex> lk(c->mu);
+      c->pump_stop = true;
+    }
+    c->cv.notify_all();
+    c->pump.join();
+  }
   if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
+  for (int i = 0; i < kDrainRing; ++i)
+    if (c->ring[i]) cudaEventDestroy(c->ring[i]);
   for (void* p : c->registered) cudaHostUnregister(p);
   cudaEvent_t evs[] = {c->ev_pack_start, c->ev_pack_end, c->ev_drain_start, c->ev_drain_end,
                        c->ev_fill_start, c->ev_fill_end, c->ev_scatter_end};
@@ -453,11 +539,8 @@ extern "C" int fc_ctx_destroy(fc_ctx* c) {
 
 static int refresh_inflight(fc_ctx* c) {
   if (c->save_inflight) {
-    cudaError_t e = cudaEventQuery(c->ev_drain_end);
-    if (e == cudaSuccess)
-      c->save_inflight = false;
-    else if (e != cudaErrorNotReady)
-      return fail(FC_ECUDA, "cudaEventQuery(drain): %s", cudaGetErrorString(e));
+    std::lock_guard<std::mutex> lk(c->mu);
+    if (c->drained_ticket >= c->ticket) c->save_inflight = false;
   }
   if (c->restore_inflight) {
     cudaError_t e = cudaEventQuery(c->ev_scatter_end);
@@ -560,7 +643,11 @@ extern "C" int fc_host_unregister(fc_ctx* c, void* host) {
   FC_GUARD(c);
   auto it = std::find(c->registered.begin(), c->registered.end(), host);
   if (it == c->registered.end()) return FC_OK;
-  // no DMA may still target the range
+  // no DMA may still target the range: let the pump finish, then the stream
+  {
+    std::unique_lock<std::mutex> lk(c->mu);
+    c->cv.wait(lk, [&] { return c->drained_ticket >= c->ticket; });
+  }
   FC_CUDA(cudaStreamSynchronize(c->copy_stream));
   c->registered.erase(it);
   FC_CUDA(cudaHostUnregister(host));
@@ -799,20 +886,21 @@ extern "C" int fc_save_async(fc_plan* p, void* host_base, void* compute_stream, 
   rc = launch_copy<0>(p, cs, FC_VARIANT_AUTO);
   if (rc) return rc;
   FC_CUDA(cudaEventRecord(c->ev_pack_end, cs));
-  FC_CUDA(cudaStreamWaitEvent(c->copy_stream, c->ev_pack_end, 0));
-  FC_CUDA(cudaEventRecord(c->ev_drain_start, c->copy_stream));
-  uint8_t* hb = static_cast<uint8_t*>(host_base);
-  for (const FcRun& r : p->runs)
-    for (uint64_t o = 0; o < r.len; o += kDmaPiece) {
-      uint64_t len = std::min<uint64_t>(kDmaPiece, r.len - o);
-      FC_CUDA(cudaMemcpyAsync(hb + r.off + o, c->arena + r.off + o, len, cudaMemcpyDeviceToHost,
-                              c->copy_stream));
-      c->n_memcpys += 1;
-    }
-  FC_CUDA(cudaEventRecord(c->ev_drain_end, c->copy_stream));
-  c->save_inflight = true;
-  c->ticket += 1;
-  if (ticket) *ticket = c->ticket;
+  // hand the drain to the pump thread (paced submission, see kDrainPiece)
+  {
+    std::lock_guard<std::mutex> lk(c->mu);
+    if (c->drain_rc != FC_OK) return fail(c->drain_rc, "%s", c->drain_err.c_str());
+    if (!c->pump.joinable()) c->pump = std::thread(pump_main, c);
+    c->ticket += 1;
+    fc_ctx::DrainJob job;
+    job.host = static_cast<uint8_t*>(host_base);
+    job.runs = p->runs;
+    job.ticket = c->ticket;
+    c->jobs.push_back(std::move(job));
+    c->save_inflight = true;
+    if (ticket) *ticket = c->ticket;
+  }
+  c->cv.notify_all();
   return FC_OK;
 }
 
@@ -832,35 +920,34 @@ extern "C" int fc_save_pack_done(fc_ctx* c, uint64_t ticket) {
   return fail(FC_ECUDA, "cudaEventQuery(pack): %s", cudaGetErrorString(e));
 }
 
+static int drain_status(fc_ctx* c, uint64_t ticket, bool wait) {
+  std::unique_lock<std::mutex> lk(c->mu);
+  if (wait) c->cv.wait(lk, [&] { return c->drained_ticket >= ticket; });
+  if (c->drained_ticket < ticket) return FC_ENOTREADY;
+  if (c->drain_rc != FC_OK) return fail(c->drain_rc, "%s", c->drain_err.c_str());
+  c->save_inflight = false;
+  return FC_OK;
+}
+
 extern "C" int fc_save_poll(fc_ctx* c, uint64_t ticket) {
   int rc = check_ticket(c, ticket, "fc_save_poll");
   if (rc) return rc;
-  FC_GUARD(c);
-  cudaError_t e = cudaEventQuery(c->ev_drain_end);
-  if (e == cudaSuccess) {
-    c->save_inflight = false;
-    return FC_OK;
-  }
-  if (e == cudaErrorNotReady) return FC_ENOTREADY;
-  return fail(FC_ECUDA, "cudaEventQuery(drain): %s", cudaGetErrorString(e));
+  return drain_status(c, ticket, false);
 }
 
 extern "C" int fc_save_wait(fc_ctx* c, uint64_t ticket) {
   int rc = check_ticket(c, ticket, "fc_save_wait");
   if (rc) return rc;
-  FC_GUARD(c);
-  FC_CUDA(cudaEventSynchronize(c->ev_drain_end));
-  c->save_inflight = false;
-  return FC_OK;
+  return drain_status(c, ticket, true);
 }
 
 extern "C" int fc_save_timings(fc_ctx* c, uint64_t ticket, float* pack_ms, float* drain_ms,
                                float* total_ms) {
   int rc = check_ticket(c, ticket, "fc_save_timings");
   if (rc) return rc;
+  rc = drain_status(c, ticket, true);
+  if (rc) return rc;
   FC_GUARD(c);
-  FC_CUDA(cudaEventSynchronize(c->ev_drain_end));
-  c->save_inflight = false;
   float t = 0.f;
   if (pack_ms) {
     FC_CUDA(cudaEventElapsedTime(&t, c->ev_pack_start, c->ev_pack_end));
@@ -874,6 +961,16 @@ extern "C" int fc_save_timings(fc_ctx* c, uint64_t ticket, float* pack_ms, float
     FC_CUDA(cudaEventElapsedTime(&t, c->ev_pack_start, c->ev_drain_end));
     *total_ms = t;
   }
+  return FC_OK;
+}
+
+extern "C" int fc_set_drain(fc_ctx* c, uint64_t piece_bytes, int depth) {
+  if (!c) return fail(FC_EINVAL, "fc_set_drain: null ctx%s%s");
+  if ((piece_bytes && piece_bytes < (64u << 10)) || depth < 0 || depth > kDrainRing)
+    return fail(FC_EINVAL, "fc_set_drain: piece >= 64 KiB, depth in [1, 8]%s%s");
+  std::lock_guard<std::mutex> lk(c->mu);
+  if (piece_bytes) c->drain_piece = piece_bytes;
+  if (depth) c->drain_depth = depth;
   return FC_OK;
 }
 

@@ -141,6 +141,13 @@ int fc_save_wait(fc_ctx* ctx, uint64_t ticket);
 int fc_save_timings(fc_ctx* ctx, uint64_t ticket, float* pack_ms, float* drain_ms,
                     float* total_ms);
 
+/* Drain pacing.  The copy engine serves D2H copies in submission order across
+ * streams, so the drain is fed by a library thread that keeps only `depth`
+ * pieces of `piece_bytes` in flight (default 2 x 32 MiB): any other D2H copy
+ * of the process (e.g. `loss.item()`) waits ~1 ms instead of the whole
+ * checkpoint.  0 keeps the current value. */
+int fc_set_drain(fc_ctx* ctx, uint64_t piece_bytes, int depth);
+
 /* ---- host-resident leaves --------------------------------------------------- */
 
 /* CPU tensors of a state_dict (optimizer step scalars, RNG state, or the whole
