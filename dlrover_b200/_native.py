@@ -48,6 +48,10 @@ _SIGNATURES = {
         [_vp, _u32, ctypes.POINTER(_vp), ctypes.POINTER(_u64), ctypes.POINTER(_u64), _u32,
          ctypes.POINTER(_vp)],
     ),
+    "fc_plan_update": (
+        ctypes.c_int,
+        [_vp, _u32, ctypes.POINTER(_vp), ctypes.POINTER(_u64), ctypes.POINTER(_u64), _vp],
+    ),
     "fc_plan_destroy": (ctypes.c_int, [_vp]),
     "fc_plan_info": (
         ctypes.c_int,
@@ -148,6 +152,9 @@ class Plan:
         self._ctx = ctx
         self._h = handle
         self.key = key
+        self._refresh_info()
+
+    def _refresh_info(self):
         lib = load_library()
         payload, items, runs, end = _u64(), _u32(), _u32(), _u64()
         _check(
@@ -165,6 +172,19 @@ class Plan:
         if not self._h:
             raise NativeError(FC_EINVAL, "Plan", "plan already destroyed")
         return self._h
+
+    def update(self, ptrs: Sequence[int], offsets: Sequence[int], nbytes: Sequence[int],
+               stream=None):
+        """Re-target the plan (stream-ordered table upload, no device sync)."""
+        n = len(ptrs)
+        a_ptr = (_vp * max(n, 1))(*[int(p) for p in ptrs])
+        a_off = (_u64 * max(n, 1))(*[int(o) for o in offsets])
+        a_len = (_u64 * max(n, 1))(*[int(b) for b in nbytes])
+        _check(load_library().fc_plan_update(self.handle, n, a_ptr, a_off, a_len,
+                                             _stream_ptr(stream)), "fc_plan_update")
+        self.key = (tuple(int(p) for p in ptrs), tuple(int(o) for o in offsets),
+                    tuple(int(b) for b in nbytes))
+        self._refresh_info()
 
     def pack(self, stream=None, variant: int = VARIANT_AUTO):
         _check(load_library().fc_pack_async(self.handle, _stream_ptr(stream), variant),

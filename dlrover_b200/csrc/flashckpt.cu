@@ -403,6 +403,9 @@ struct fc_ctx {
   int drain_rc = FC_OK;         // sticky error of the pump
   std::string drain_err;
   cudaEvent_t ring[kDrainRing] = {};
+  // device/pinned buffers whose cudaFree (a device-wide sync) is deferred to a
+  // moment that synchronises anyway
+  std::vector<void*> dead_dev, dead_pinned;
   uint64_t drain_piece = kDrainPiece;
   int drain_depth = kDrainDepth;
 };
@@ -450,14 +453,24 @@ static void pump_main(fc_ctx* c) {
   }
 }
 
+// One device-resident work table + its pinned staging copy (grow-only).
+struct FcTable {
+  FcItem* dev = nullptr;
+  FcItem* pinned = nullptr;
+  uint32_t cap = 0;
+  uint32_t n = 0;
+};
+
 struct fc_plan {
   fc_ctx* ctx = nullptr;
-  FcItem* d_all = nullptr;    // every byte, <= chunk pieces (LSU variant)
-  FcItem* d_bulk = nullptr;   // 16-B congruent bodies (TMA variant)
-  FcItem* d_resid = nullptr;  // heads, tails and non-congruent ranges (TMA variant)
-  uint32_t n_all = 0, n_bulk = 0, n_resid = 0;
+  FcTable all;    // every byte, <= chunk pieces (LSU variant)
+  FcTable bulk;   // 16-B congruent bodies (TMA variant)
+  FcTable resid;  // heads, tails and non-congruent ranges (TMA variant)
   uint64_t payload = 0, arena_end = 0;
+  uint32_t chunk = kDefaultChunk;
   std::vector<FcRun> runs;
+  cudaEvent_t ev_upload = nullptr;  // last table upload
+  cudaEvent_t ev_last_use = nullptr;  // last kernel that read the tables
 };
 
 struct DeviceGuard {
@@ -533,6 +546,8 @@ extern "C" int fc_ctx_destroy(fc_ctx* c) {
     if (ev) cudaEventDestroy(ev);
   if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
   if (c->arena) cudaFree(c->arena);
+  for (void* q : c->dead_dev) cudaFree(q);
+  for (void* q : c->dead_pinned) cudaFreeHost(q);
   delete c;
   return FC_OK;
 }
@@ -565,6 +580,10 @@ extern "C" int fc_arena_reserve(fc_ctx* c, uint64_t bytes) {
     c->arena = nullptr;
     c->arena_bytes = 0;
   }
+  for (void* q : c->dead_dev) cudaFree(q);  // cudaFree above synchronised already
+  for (void* q : c->dead_pinned) cudaFreeHost(q);
+  c->dead_dev.clear();
+  c->dead_pinned.clear();
   // +32: the shifted load path may read one aligned 16-B word past the end.
   uint64_t want = ((bytes + 32 + 511) / 512) * 512;
   cudaError_t e = cudaMalloc(&c->arena, want);
@@ -674,63 +693,71 @@ static void split_range(std::vector<FcItem>& out, uint64_t tptr, uint64_t off, u
   }
 }
 
-static int upload(FcItem** d, const std::vector<FcItem>& v) {
-  *d = nullptr;
+// Put `v` into table `t` (device copy ordered on `s`).  sync=true: blocking
+// cudaMemcpy from the vector (plan creation).  sync=false: staged through the
+// table's pinned buffer and cudaMemcpyAsync on `s`, never a device-wide sync.
+static int table_set(fc_ctx* c, FcTable& t, const std::vector<FcItem>& v, cudaStream_t s,
+                     bool sync) {
+  t.n = (uint32_t)v.size();
   if (v.empty()) return FC_OK;
-  cudaError_t e = cudaMalloc(d, v.size() * sizeof(FcItem));
-  if (e != cudaSuccess) {
-    (void)cudaGetLastError();
-    return fail(FC_ENOMEM, "cudaMalloc(plan): %s", cudaGetErrorString(e));
+  if (v.size() > t.cap) {
+    uint32_t cap = (uint32_t)std::min<uint64_t>(0xFFFFFFF0ull, v.size() + v.size() / 4 + 16);
+    FcItem* nd = nullptr;
+    FcItem* np = nullptr;
+    cudaError_t e = cudaMalloc(&nd, (size_t)cap * sizeof(FcItem));
+    if (e == cudaSuccess) e = cudaHostAlloc(&np, (size_t)cap * sizeof(FcItem), cudaHostAllocDefault);
+    if (e != cudaSuccess) {
+      (void)cudaGetLastError();
+      if (nd) c->dead_dev.push_back(nd);
+      return fail(FC_ENOMEM, "plan table alloc: %s", cudaGetErrorString(e));
+    }
+    if (t.dev) c->dead_dev.push_back(t.dev);  // may still be read by a queued kernel
+    if (t.pinned) c->dead_pinned.push_back(t.pinned);
+    t.dev = nd;
+    t.pinned = np;
+    t.cap = cap;
   }
-  FC_CUDA(cudaMemcpy(*d, v.data(), v.size() * sizeof(FcItem), cudaMemcpyHostToDevice));
+  const size_t bytes = v.size() * sizeof(FcItem);
+  if (sync) {
+    FC_CUDA(cudaMemcpy(t.dev, v.data(), bytes, cudaMemcpyHostToDevice));
+  } else {
+    memcpy(t.pinned, v.data(), bytes);
+    FC_CUDA(cudaMemcpyAsync(t.dev, t.pinned, bytes, cudaMemcpyHostToDevice, s));
+  }
   return FC_OK;
 }
 
-extern "C" int fc_plan_create(fc_ctx* c, uint32_t n, const void* const* dev_ptrs,
-                              const uint64_t* arena_off, const uint64_t* nbytes,
-                              uint32_t chunk_bytes, fc_plan** out) {
-  if (!c || !out || (n && (!dev_ptrs || !arena_off || !nbytes)))
-    return fail(FC_EINVAL, "fc_plan_create: null argument%s%s");
-  if (chunk_bytes == 0) chunk_bytes = kDefaultChunk;
-  if (chunk_bytes < 4096 || (chunk_bytes & 127u) || chunk_bytes > (1u << 30))
-    return fail(FC_EINVAL, "fc_plan_create: chunk_bytes must be a multiple of 128 in [4 KiB, 1 GiB]%s%s");
-  FC_GUARD(c);
-  fc_plan* p = new (std::nothrow) fc_plan();
-  if (!p) return fail(FC_ENOMEM, "fc_plan_create: host alloc%s%s");
-  p->ctx = c;
-
-  // runs + overlap check on the arena side
-  std::vector<FcRun> ranges;
+// (Re)build the plan's runs and work tables from n ranges.
+static int plan_fill(fc_plan* p, uint32_t n, const void* const* dev_ptrs,
+                     const uint64_t* arena_off, const uint64_t* nbytes, cudaStream_t s,
+                     bool sync) {
+  fc_ctx* c = p->ctx;
+  const uint32_t chunk_bytes = p->chunk;
+  uint64_t payload = 0, arena_end = 0;
+  std::vector<FcRun> ranges, runs;
   ranges.reserve(n);
   for (uint32_t i = 0; i < n; ++i) {
     if (nbytes[i] == 0) continue;
-    if (!dev_ptrs[i]) {
-      delete p;
-      return fail(FC_EINVAL, "fc_plan_create: null device pointer for a non-empty tensor%s%s");
-    }
-    if (arena_off[i] + nbytes[i] < arena_off[i]) {
-      delete p;
-      return fail(FC_EINVAL, "fc_plan_create: offset overflow%s%s");
-    }
+    if (!dev_ptrs[i])
+      return fail(FC_EINVAL, "plan: null device pointer for a non-empty tensor%s%s");
+    if (arena_off[i] + nbytes[i] < arena_off[i]) return fail(FC_EINVAL, "plan: offset overflow%s%s");
     ranges.push_back({arena_off[i], nbytes[i]});
-    p->payload += nbytes[i];
-    p->arena_end = std::max(p->arena_end, arena_off[i] + nbytes[i]);
+    payload += nbytes[i];
+    arena_end = std::max(arena_end, arena_off[i] + nbytes[i]);
   }
   std::sort(ranges.begin(), ranges.end(),
             [](const FcRun& a, const FcRun& b) { return a.off < b.off; });
   for (const FcRun& r : ranges) {
-    if (!p->runs.empty()) {
-      FcRun& last = p->runs.back();
-      if (r.off < last.off + last.len) {
-        delete p;
-        return fail(FC_EINVAL, "fc_plan_create: tensors overlap in the arena%s%s");
-      }
+    if (!runs.empty()) {
+      FcRun& last = runs.back();
+      if (r.off < last.off + last.len)
+        return fail(FC_EINVAL, "plan: tensors overlap in the arena%s%s");
       if (r.off == last.off + last.len) {
         last.len += r.len;
         continue;
       }
     }
-    p->runs.push_back(r);
+    runs.push_back(r);
   }
 
   std::vector<FcItem> all, bulk, resid;
@@ -751,16 +778,37 @@ extern "C" int fc_plan_create(fc_ctx* c, uint32_t n, const void* const* dev_ptrs
     uint64_t tail = nb - head - body;
     if (tail) split_range(resid, tp + head + body, off + head + body, tail, chunk_bytes);
   }
-  if (all.size() > 0xFFFFFFF0ull) {
-    delete p;
-    return fail(FC_EINVAL, "fc_plan_create: too many work items%s%s");
+  if (all.size() > 0xFFFFFFF0ull) return fail(FC_EINVAL, "plan: too many work items%s%s");
+  int rc = table_set(c, p->all, all, s, sync);
+  if (!rc) rc = table_set(c, p->bulk, bulk, s, sync);
+  if (!rc) rc = table_set(c, p->resid, resid, s, sync);
+  if (rc) return rc;
+  p->payload = payload;
+  p->arena_end = arena_end;
+  p->runs.swap(runs);
+  return FC_OK;
+}
+
+extern "C" int fc_plan_create(fc_ctx* c, uint32_t n, const void* const* dev_ptrs,
+                              const uint64_t* arena_off, const uint64_t* nbytes,
+                              uint32_t chunk_bytes, fc_plan** out) {
+  if (!c || !out || (n && (!dev_ptrs || !arena_off || !nbytes)))
+    return fail(FC_EINVAL, "fc_plan_create: null argument%s%s");
+  if (chunk_bytes == 0) chunk_bytes = kDefaultChunk;
+  if (chunk_bytes < 4096 || (chunk_bytes & 127u) || chunk_bytes > (1u << 30))
+    return fail(FC_EINVAL, "fc_plan_create: chunk_bytes must be a multiple of 128 in [4 KiB, 1 GiB]%s%s");
+  FC_GUARD(c);
+  fc_plan* p = new (std::nothrow) fc_plan();
+  if (!p) return fail(FC_ENOMEM, "fc_plan_create: host alloc%s%s");
+  p->ctx = c;
+  p->chunk = chunk_bytes;
+  cudaError_t e = cudaEventCreateWithFlags(&p->ev_upload, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->ev_last_use, cudaEventDisableTiming);
+  if (e != cudaSuccess) {
+    fc_plan_destroy(p);
+    return fail(FC_ECUDA, "fc_plan_create: %s", cudaGetErrorString(e));
   }
-  p->n_all = (uint32_t)all.size();
-  p->n_bulk = (uint32_t)bulk.size();
-  p->n_resid = (uint32_t)resid.size();
-  int rc = upload(&p->d_all, all);
-  if (!rc) rc = upload(&p->d_bulk, bulk);
-  if (!rc) rc = upload(&p->d_resid, resid);
+  int rc = plan_fill(p, n, dev_ptrs, arena_off, nbytes, nullptr, /*sync=*/true);
   if (rc) {
     fc_plan_destroy(p);
     return rc;
@@ -769,14 +817,41 @@ extern "C" int fc_plan_create(fc_ctx* c, uint32_t n, const void* const* dev_ptrs
   return FC_OK;
 }
 
+extern "C" int fc_plan_update(fc_plan* p, uint32_t n, const void* const* dev_ptrs,
+                              const uint64_t* arena_off, const uint64_t* nbytes, void* stream) {
+  if (!p || (n && (!dev_ptrs || !arena_off || !nbytes)))
+    return fail(FC_EINVAL, "fc_plan_update: null argument%s%s");
+  fc_ctx* c = p->ctx;
+  FC_GUARD(c);
+  int rc = refresh_inflight(c);
+  if (rc) return rc;
+  if (c->save_inflight || c->restore_inflight)
+    return fail(FC_EBUSY, "fc_plan_update: a save/restore is still in flight%s%s");
+  // the staging buffers are reused: the previous upload must have executed
+  FC_CUDA(cudaEventSynchronize(p->ev_upload));
+  cudaStream_t s = (cudaStream_t)stream;
+  // a kernel of this plan queued on ANOTHER stream must not see the new table
+  FC_CUDA(cudaStreamWaitEvent(s, p->ev_last_use, 0));
+  rc = plan_fill(p, n, dev_ptrs, arena_off, nbytes, s, /*sync=*/false);
+  if (rc) return rc;
+  FC_CUDA(cudaEventRecord(p->ev_upload, s));
+  return FC_OK;
+}
+
 extern "C" int fc_plan_destroy(fc_plan* p) {
   if (!p) return FC_OK;
-  DeviceGuard g(p->ctx->device);
-  // the kernels that read the tables may still be queued
-  cudaDeviceSynchronize();
-  if (p->d_all) cudaFree(p->d_all);
-  if (p->d_bulk) cudaFree(p->d_bulk);
-  if (p->d_resid) cudaFree(p->d_resid);
+  fc_ctx* c = p->ctx;
+  DeviceGuard g(c->device);
+  // Queued kernels may still read the tables: wait for the last one (not for
+  // the whole device) and defer the cudaFree (which would sync everything).
+  if (p->ev_last_use) cudaEventSynchronize(p->ev_last_use);
+  if (p->ev_upload) cudaEventSynchronize(p->ev_upload);
+  for (FcTable* t : {&p->all, &p->bulk, &p->resid}) {
+    if (t->dev) c->dead_dev.push_back(t->dev);
+    if (t->pinned) c->dead_pinned.push_back(t->pinned);
+  }
+  if (p->ev_upload) cudaEventDestroy(p->ev_upload);
+  if (p->ev_last_use) cudaEventDestroy(p->ev_last_use);
   delete p;
   return FC_OK;
 }
@@ -785,7 +860,7 @@ extern "C" int fc_plan_info(const fc_plan* p, uint64_t* payload_bytes, uint32_t*
                             uint32_t* n_runs, uint64_t* arena_end) {
   if (!p) return fail(FC_EINVAL, "fc_plan_info: null plan%s%s");
   if (payload_bytes) *payload_bytes = p->payload;
-  if (n_items) *n_items = p->n_all;
+  if (n_items) *n_items = p->all.n;
   if (n_runs) *n_runs = (uint32_t)p->runs.size();
   if (arena_end) *arena_end = p->arena_end;
   return FC_OK;
@@ -853,12 +928,18 @@ static int launch_copy(fc_plan* p, cudaStream_t s, int variant) {
   if (p->arena_end > c->arena_bytes)
     return fail(FC_EINVAL, "arena smaller than the plan: call fc_arena_reserve first%s%s");
   if (variant == FC_VARIANT_AUTO) variant = c->variant;
+  // tables may have been (re)uploaded on another stream
+  FC_CUDA(cudaStreamWaitEvent(s, p->ev_upload, 0));
+  int rc;
   if (variant == FC_VARIANT_TMA) {
-    int rc = launch_tma<DIR>(c, p->d_bulk, p->n_bulk, s);
-    if (rc) return rc;
-    return launch_lsu<DIR>(c, p->d_resid, p->n_resid, s);
+    rc = launch_tma<DIR>(c, p->bulk.dev, p->bulk.n, s);
+    if (!rc) rc = launch_lsu<DIR>(c, p->resid.dev, p->resid.n, s);
+  } else {
+    rc = launch_lsu<DIR>(c, p->all.dev, p->all.n, s);
   }
-  return launch_lsu<DIR>(c, p->d_all, p->n_all, s);
+  if (rc) return rc;
+  FC_CUDA(cudaEventRecord(p->ev_last_use, s));
+  return FC_OK;
 }
 
 extern "C" int fc_pack_async(fc_plan* p, void* stream, int variant) {

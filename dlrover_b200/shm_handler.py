@@ -183,8 +183,7 @@ class _DeviceStager:
         self.device_index = device_index
         self.ctx = native.get_context(device_index)
         self._registered_addr = 0
-        # most-recent-first; 2 entries so a restore plan does not evict the save plan
-        self._plans: List[native.Plan] = []
+        self._plans: Dict[str, native.Plan] = {}  # role -> plan
         self.register_seconds = 0.0
 
     def attach(self, shm: SharedMemory):
@@ -208,8 +207,12 @@ class _DeviceStager:
                 logger.warning(f"host_unregister: {e}")
             self._registered_addr = 0
 
-    def plan_for(self, ranges: List[Tuple[torch.Tensor, int, int]], keepalive: list):
-        """ranges: (tensor, segment offset, nbytes) per device-resident leaf."""
+    def plan_for(self, ranges: List[Tuple[torch.Tensor, int, int]], keepalive: list,
+                 role: str = "save", stream=None):
+        """ranges: (tensor, segment offset, nbytes) per device-resident leaf.
+        One plan object per role ("save" / "restore"); when the tensors moved
+        (FSDP hands out fresh ones on every state_dict()) the plan is
+        re-targeted in place with a stream-ordered table upload."""
         ptrs, offs, lens = [], [], []
         for t, off, nbytes in ranges:
             if not t.is_contiguous():
@@ -221,21 +224,19 @@ class _DeviceStager:
             offs.append(off)
             lens.append(nbytes)
         key = (tuple(ptrs), tuple(offs), tuple(lens))
-        for i, p in enumerate(self._plans):
-            if p.key == key:
-                if i:
-                    self._plans.insert(0, self._plans.pop(i))
-                return p
+        plan = self._plans.get(role)
+        if plan is not None and plan.key == key:
+            return plan
         end = max((o + n for o, n in zip(offs, lens)), default=0)
         self.ctx.arena_reserve(end)
-        plan = self.ctx.plan(ptrs, offs, lens)
-        self._plans.insert(0, plan)
-        while len(self._plans) > 2:
-            self._plans.pop().destroy()
+        if plan is None:
+            plan = self._plans[role] = self.ctx.plan(ptrs, offs, lens)
+        else:
+            plan.update(ptrs, offs, lens, stream)
         return plan
 
     def close(self):
-        for p in self._plans:
+        for p in self._plans.values():
             p.destroy()
         self._plans.clear()
         self.detach()
@@ -416,9 +417,9 @@ class SharedMemoryHandler:
         if device_ranges:
             stager = self._stager_for([r[0] for r in device_ranges])
             stager.attach(self.shared_memory)
-            plan = stager.plan_for(device_ranges, keepalive)
             if stream is None:
                 stream = torch.cuda.current_stream(stager.device_index)
+            plan = stager.plan_for(device_ranges, keepalive, role="save", stream=stream)
             ticket = plan.save_async(self.shared_memory.address, stream)
             ctx = stager.ctx
         pending = PendingSave(ctx, ticket, finish or (lambda: None), keepalive)
@@ -564,10 +565,11 @@ class SharedMemoryHandler:
                         raise ValueError("restore_into needs contiguous CUDA targets")
                 stager = self._stager_for([t for t, _ in device_pairs])
                 stager.attach(self.shared_memory)
-                plan = stager.plan_for(
-                    [(t, m.offset, m.numel * m.element_size) for t, m in device_pairs], [])
                 if stream is None:
                     stream = torch.cuda.current_stream(stager.device_index)
+                plan = stager.plan_for(
+                    [(t, m.offset, m.numel * m.element_size) for t, m in device_pairs], [],
+                    role="restore", stream=stream)
                 plan.restore_async(self.shared_memory.address, stream)
                 stager.ctx.restore_wait()
                 fill, scatter, _ = stager.ctx.restore_timings()

@@ -97,6 +97,13 @@ int fc_host_unregister(fc_ctx* ctx, void* host);
 int fc_plan_create(fc_ctx* ctx, uint32_t n, const void* const* dev_ptrs,
                    const uint64_t* arena_off, const uint64_t* nbytes,
                    uint32_t chunk_bytes, fc_plan** out);
+/* Re-target an existing plan at a new set of ranges (frameworks that hand out
+ * fresh tensors on every state_dict() call, e.g. FSDP): the tables are rebuilt
+ * on the host, staged in pinned memory and uploaded with cudaMemcpyAsync on
+ * `stream` — ordered before the next kernel of this plan, never a device-wide
+ * synchronisation.  FC_EBUSY while a save/restore of the context is in flight. */
+int fc_plan_update(fc_plan* plan, uint32_t n, const void* const* dev_ptrs,
+                   const uint64_t* arena_off, const uint64_t* nbytes, void* stream);
 int fc_plan_destroy(fc_plan* plan);
 /* total payload bytes, number of work items, number of merged arena runs,
  * end offset (max arena_off+nbytes) */

@@ -186,3 +186,37 @@ def test_busy_and_errors(cuda_device):
     with pytest.raises(native.NativeError):
         big.pack()  # arena smaller than plan
     big.destroy()
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
+def test_plan_update_retargets_without_recreating(cuda_device, variant):
+    """fc_plan_update: same plan object, new tensors/offsets/sizes (grow and
+    shrink), stream-ordered upload."""
+    ctx = native.get_context(0)
+    g = torch.Generator().manual_seed(21)
+    a = [torch.randint(0, 256, (n,), dtype=torch.uint8, generator=g).cuda()
+         for n in (1000, 70_000, 33)]
+    ctx.arena_reserve(1 << 22)
+    plan = ctx.plan([t.data_ptr() for t in a], [0, 1000, 71_000], [t.numel() for t in a], 4096)
+    stream = torch.cuda.current_stream()
+    plan.pack(stream, variant)
+    b = [torch.randint(0, 256, (n,), dtype=torch.uint8, generator=g).cuda()
+         for n in (5, 1 << 20, 4097, 300_000, 16)]
+    offs, o = [], 3
+    for t in b:
+        offs.append(o)
+        o += t.numel()
+    plan.update([t.data_ptr() for t in b], offs, [t.numel() for t in b], stream)
+    assert plan.payload_bytes == sum(t.numel() for t in b) and plan.arena_end == o
+    plan.pack(stream, variant)
+    torch.cuda.synchronize()
+    got = _arena_bytes(ctx, o)
+    want = oracle.pack_ranges([oracle.tensor_bytes(t) for t in b], offs, o)
+    assert np.array_equal(got[3:], want[3:])
+    # shrink again
+    plan.update([a[1].data_ptr()], [64], [a[1].numel()], stream)
+    plan.pack(stream, variant)
+    torch.cuda.synchronize()
+    got = _arena_bytes(ctx, 64 + a[1].numel())
+    assert np.array_equal(got[64:], oracle.tensor_bytes(a[1]))
+    plan.destroy()
