@@ -372,5 +372,9 @@ def get_context(device: int) -> Context:
             forced = os.getenv("DLROVER_B200_VARIANT", "").lower()
             if forced in ("lsu", "tma"):  # profiling / A-B runs only
                 ctx.set_variant(VARIANT_LSU if forced == "lsu" else VARIANT_TMA)
+            piece = int(os.getenv("DLROVER_B200_DRAIN_PIECE_MB", "0") or 0)
+            depth = int(os.getenv("DLROVER_B200_DRAIN_DEPTH", "0") or 0)
+            if piece or depth:  # tuning runs only
+                ctx.set_drain(piece << 20, depth)
             _contexts[device] = ctx
         return ctx

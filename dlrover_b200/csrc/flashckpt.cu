@@ -97,13 +97,16 @@ constexpr int kLsuThreads = 256;
 constexpr int kLsuUnroll = 4;
 constexpr uint32_t kDefaultChunk = 256u << 10;      // work-item size
 constexpr uint64_t kDmaPiece = 256ull << 20;        // restore fill memcpy size
-// Drain pacing: the D2H copy engine serves copies in submission order across
-// streams, so a drain submitted as one batch delays every unrelated D2H copy
-// of the process (a `loss.item()`!) until the whole checkpoint has left the
-// device.  The pump thread therefore keeps only kDrainDepth pieces of
-// kDrainPiece bytes in flight: a foreign copy waits for <= ~1 ms of drain.
+// Drain pacing.  Measured on B200 (tools/d2h_probe2.py, profiles/r01_d2h_pacing.md):
+// while a stream has ANOTHER D2H copy queued behind the one in flight, the
+// copy engine keeps serving that stream, and a small D2H copy from any other
+// stream of the process (a `loss.item()`!) starves until the whole checkpoint
+// has left the device (145-290 ms).  With exactly ONE piece in flight the
+// engine's queue empties for a moment after every piece and the foreign copy
+// goes through in ~0.4 ms, at 54.5 instead of 55.2 GB/s of drain throughput.
+// The pump thread therefore submits piece k+1 only after piece k completed.
 constexpr uint64_t kDrainPiece = 32ull << 20;
-constexpr int kDrainDepth = 2;
+constexpr int kDrainDepth = 1;
 constexpr int kDrainRing = 8;
 
 // ------------------------------------------------------------ device helpers --

@@ -148,11 +148,12 @@ int fc_save_wait(fc_ctx* ctx, uint64_t ticket);
 int fc_save_timings(fc_ctx* ctx, uint64_t ticket, float* pack_ms, float* drain_ms,
                     float* total_ms);
 
-/* Drain pacing.  The copy engine serves D2H copies in submission order across
- * streams, so the drain is fed by a library thread that keeps only `depth`
- * pieces of `piece_bytes` in flight (default 2 x 32 MiB): any other D2H copy
- * of the process (e.g. `loss.item()`) waits ~1 ms instead of the whole
- * checkpoint.  0 keeps the current value. */
+/* Drain pacing.  While a stream has another D2H copy queued behind the one in
+ * flight the copy engine keeps serving it, and every other D2H copy of the
+ * process (e.g. `loss.item()`) starves until the whole checkpoint has left the
+ * device.  The drain is therefore fed by a library thread that submits piece
+ * k+1 only after piece k completed (default: depth 1 x 32 MiB; a foreign copy
+ * then gets through in ~0.4 ms).  0 keeps the current value. */
 int fc_set_drain(fc_ctx* ctx, uint64_t piece_bytes, int depth);
 
 /* ---- host-resident leaves --------------------------------------------------- */
