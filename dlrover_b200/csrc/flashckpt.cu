@@ -36,7 +36,6 @@
 #include <unistd.h>
 
 #include <algorithm>
-#include <chrono>
 #include <condition_variable>
 #include <deque>
 #include <mutex>
@@ -414,25 +413,6 @@ struct fc_ctx {
   int drain_depth = kDrainDepth;
 };
 
-// Wait for a piece with microsecond wake-up but without spinning a core for
-// its whole duration: sleep through ~3/4 of the expected time (EMA of the
-// previous pieces), then poll the event.
-static cudaError_t wait_piece(cudaEvent_t ev, double* est_us) {
-  using clk = std::chrono::steady_clock;
-  const auto t0 = clk::now();
-  if (*est_us > 200.0)
-    std::this_thread::sleep_for(std::chrono::microseconds((long)(*est_us * 0.75)));
-  cudaError_t e;
-  while ((e = cudaEventQuery(ev)) == cudaErrorNotReady) {
-#if defined(__x86_64__)
-    __builtin_ia32_pause();
-#endif
-  }
-  const double us = std::chrono::duration<double, std::micro>(clk::now() - t0).count();
-  *est_us = *est_us <= 0.0 ? us : 0.7 * *est_us + 0.3 * us;
-  return e;
-}
-
 static void pump_main(fc_ctx* c) {
   cudaSetDevice(c->device);
   for (;;) {
@@ -448,11 +428,10 @@ static void pump_main(fc_ctx* c) {
     if (e == cudaSuccess) e = cudaEventRecord(c->ev_drain_start, c->copy_stream);
     const int depth = std::max(1, std::min(c->drain_depth, kDrainRing));
     uint64_t k = 0, copies = 0;
-    double est_us = 0.0;  // observed wait per piece (equal-sized pieces)
     for (const FcRun& r : job.runs) {
       for (uint64_t o = 0; o < r.len && e == cudaSuccess; o += c->drain_piece) {
         const uint64_t len = std::min<uint64_t>(c->drain_piece, r.len - o);
-        if (k >= (uint64_t)depth) e = wait_piece(c->ring[k % depth], &est_us);  // piece k-depth
+        if (k >= (uint64_t)depth) e = cudaEventSynchronize(c->ring[k % depth]);  // piece k-depth
         if (e == cudaSuccess)
           e = cudaMemcpyAsync(job.host + r.off + o, c->arena + r.off + o, len,
                               cudaMemcpyDeviceToHost, c->copy_stream);
@@ -538,9 +517,14 @@ extern "C" int fc_ctx_create(int device, fc_ctx** out) {
                         &c->ev_fill_start, &c->ev_fill_end,  &c->ev_scatter_end};
   for (cudaEvent_t* ev : evs)
     if (e == cudaSuccess) e = cudaEventCreate(ev);
+  // FC_DRAIN_SPIN=1: the pump spin-waits between pieces (lower wake-up latency,
+  // one busy host core while a checkpoint drains); default: blocking wait.
+  const char* spin_env = getenv("FC_DRAIN_SPIN");
+  const bool drain_spin = spin_env && spin_env[0] == '1';
   for (int i = 0; i < kDrainRing; ++i)
     if (e == cudaSuccess)
-      e = cudaEventCreateWithFlags(&c->ring[i], cudaEventDisableTiming);
+      e = cudaEventCreateWithFlags(
+          &c->ring[i], cudaEventDisableTiming | (drain_spin ? 0 : cudaEventBlockingSync));
   if (e != cudaSuccess) {
     fc_ctx_destroy(c);
     return fail(FC_ECUDA, "fc_ctx_create: %s", cudaGetErrorString(e));
