@@ -1,0 +1,95 @@
+"""BASELINE.json full-size case on the GPU (Llama-3-8B bf16, 16.06 GB): parity
+through size-independent properties — a checksum of per-tensor checksums of the
+segment equals the same checksum computed on the device, spot byte-compares,
+and save -> zero -> restore -> torch.equal on every tensor; plus the AdamW-style
+misaligned layout at 1/8 size."""
+
+import numpy as np
+import pytest
+import torch
+
+from dlrover_b200 import shapes
+from dlrover_b200.shm_handler import DLROVER_CKPT_CONFIG_KEY, CheckpointConfig, SharedMemoryHandler
+from oracle import shm_layout as oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def _checksum_device(t):
+    v = t.reshape(-1).view(torch.int16).to(torch.int64)
+    return int(v.sum().item()) & 0xFFFFFFFFFFFF
+
+
+def _checksum_host(buf, off, nbytes):
+    v = np.frombuffer(buf, dtype=np.int16, count=nbytes // 2, offset=off)
+    return int(v.astype(np.int64).sum()) & 0xFFFFFFFFFFFF
+
+
+def test_llama3_8b_bf16_full_size(cuda_device, run_env):
+    sd = shapes.build_state_dict(shapes.llama3_8b_shapes(), torch.bfloat16, cuda_device)
+    assert len(sd) == 291
+    assert shapes.payload_bytes(sd) == 16_060_522_496
+    handler = SharedMemoryHandler(0, host=True)
+    full = {"model_states": sd,
+            DLROVER_CKPT_CONFIG_KEY: CheckpointConfig(step=1, paths={"model_states": "/x"})}
+    handler.save_state_dict(full)
+    assert handler.shared_memory.size == 16_060_522_496
+    meta = handler.metadata.get()["model_states"]
+    # reference layout: offsets are the running sum, in key order
+    want_meta, total = oracle.plan_layout({"model_states": sd})
+    assert total == handler.shared_memory.size
+    off = 0
+    for k, t in sd.items():
+        m = meta[k]
+        assert m.offset == off == want_meta["model_states"][k].offset
+        off += t.numel() * 2
+    buf = handler.shared_memory.buf
+    dev_sum = host_sum = 0
+    for i, (k, t) in enumerate(sd.items()):
+        m = meta[k]
+        dev_sum = (dev_sum * 31 + _checksum_device(t)) & 0xFFFFFFFFFFFF
+        host_sum = (host_sum * 31 + _checksum_host(buf, m.offset, t.numel() * 2)) & 0xFFFFFFFFFFFF
+        if i % 37 == 0:  # spot byte-compare: head and tail of the tensor
+            n = min(t.numel() * 2, 1 << 16)
+            flat = t.reshape(-1).view(torch.uint8)
+            assert bytes(buf[m.offset:m.offset + n]) == flat[:n].cpu().numpy().tobytes()
+            end = m.offset + t.numel() * 2
+            assert bytes(buf[end - n:end]) == flat[-n:].cpu().numpy().tobytes()
+    assert dev_sum == host_sum
+    # restore into zeroed live tensors
+    keep = {k: _checksum_device(t) for k, t in sd.items()}
+    probe = {k: sd[k].clone() for k in list(sd)[:3] + list(sd)[-2:]}
+    for t in sd.values():
+        t.zero_()
+    stats = handler.restore_into({"model_states": sd})
+    assert stats["device_bytes"] == 16_060_522_496
+    for k, t in sd.items():
+        assert _checksum_device(t) == keep[k], k
+    for k, t in probe.items():
+        assert torch.equal(sd[k], t)
+    del buf
+    handler.unlink()
+    handler.close()
+
+
+def test_adamw_layout_misaligned_eighth_size(cuda_device, run_env):
+    """fp32 moments behind 4-byte step scalars: 3/4 of the bytes take the
+    byte-funnel path.  Compared byte-for-byte with the oracle image."""
+    params = shapes.build_state_dict(
+        shapes.scale_shapes(shapes.llama3_8b_shapes()[:12], 0.125), torch.bfloat16, cuda_device)
+    optim = shapes.adamw_state(params)
+    sd = {"model": params, "optimizer": optim}
+    handler = SharedMemoryHandler(0, host=True)
+    full = {"model_states": sd,
+            DLROVER_CKPT_CONFIG_KEY: CheckpointConfig(step=1, paths={"model_states": "/x"})}
+    handler.save_state_dict(full)
+    _, want = oracle.serialize({"model_states": sd})
+    got = np.frombuffer(handler.shared_memory.buf, dtype=np.uint8)
+    assert got.size == want.size
+    assert np.array_equal(got, want)
+    offs = [m.offset % 16 for m in oracle.flatten_tensor_metas(
+        oracle.plan_layout({"model_states": sd})[0])]
+    assert {4, 8, 12} <= set(offs)  # the layout really is misaligned
+    del got
+    handler.unlink()
+    handler.close()
