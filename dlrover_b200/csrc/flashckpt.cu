@@ -146,26 +146,50 @@ __device__ __forceinline__ uint4 funnel16(const uint4& lo, const uint4& hi, uint
   return o;
 }
 
+__device__ __forceinline__ uint4 shfl_down1(const uint4& v) {
+  uint4 o;
+  o.x = __shfl_down_sync(0xffffffffu, v.x, 1);
+  o.y = __shfl_down_sync(0xffffffffu, v.y, 1);
+  o.z = __shfl_down_sync(0xffffffffu, v.z, 1);
+  o.w = __shfl_down_sync(0xffffffffu, v.w, 1);
+  return o;
+}
+
 // Copy nvec 16-B vectors: dst is 16-B aligned, src = abase + r (abase aligned).
+// Output vector i needs the aligned words W[i] and W[i+1].  Every lane loads
+// its W[i] ONCE (coalesced 512 B per warp) and takes W[i+1] from its right
+// neighbour with a shuffle; only lane 31 loads the extra halo word.  (Loading
+// both words per lane re-fetched the shared sectors: ncu showed 18.7 GB of
+// DRAM reads for 16.06 GB of payload, profiles/r01_shifted_path.md.)
 template <int Q>
 __device__ __forceinline__ void copy_shifted(const uint4* __restrict__ abase,
                                              uint4* __restrict__ dst, uint32_t nvec,
                                              uint32_t sh) {
   constexpr int T = kLsuThreads, U = kLsuUnroll;
-  uint32_t i = threadIdx.x;
-  for (; i + (U - 1) * T < nvec; i += U * T) {
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t wbase = threadIdx.x - lane;  // first vector of this warp in the block row
+  // W[nvec] (the halo of the last vector) shares a 16-B word with valid source
+  // bytes, so indices <= nvec are readable.
+  for (uint32_t base = wbase; base < nvec; base += U * T) {  // warp-uniform bounds
     uint4 lo[U], hi[U];
+    // all global loads first (body + lane-31 halos), so one memory latency is
+    // exposed per iteration, not two
 #pragma unroll
     for (int j = 0; j < U; ++j) {
-      lo[j] = ldg_cached(abase + i + j * T);
-      hi[j] = ldg_cached(abase + i + j * T + 1);
+      const uint32_t idx = base + j * T + lane;
+      lo[j] = idx <= nvec ? ldg_stream(abase + idx) : make_uint4(0, 0, 0, 0);
+      hi[j] = (lane == 31u && idx < nvec) ? ldg_cached(abase + idx + 1) : make_uint4(0, 0, 0, 0);
     }
 #pragma unroll
-    for (int j = 0; j < U; ++j) stg_stream(dst + i + j * T, funnel16<Q>(lo[j], hi[j], sh));
-  }
-  for (; i < nvec; i += T) {
-    uint4 lo = ldg_cached(abase + i), hi = ldg_cached(abase + i + 1);
-    stg_stream(dst + i, funnel16<Q>(lo, hi, sh));
+    for (int j = 0; j < U; ++j) {
+      const uint4 nb = shfl_down1(lo[j]);
+      if (lane != 31u) hi[j] = nb;
+    }
+#pragma unroll
+    for (int j = 0; j < U; ++j) {
+      const uint32_t idx = base + j * T + lane;
+      if (idx < nvec) stg_stream(dst + idx, funnel16<Q>(lo[j], hi[j], sh));
+    }
   }
 }
 
@@ -365,6 +389,158 @@ fc_copy_tma(const FcItem* __restrict__ items, uint32_t n_items, uint8_t* __restr
   bulk_wait_all();
 }
 
+// ---- TMA-fed byte-shift kernel ------------------------------------------------
+// For ranges whose source and destination are NOT congruent mod 16 (everything
+// behind a 4-byte optimizer `step` scalar in the reference's unpadded layout).
+// Global traffic is all bulk-async and fully sector-efficient: the aligned
+// source span of each 16 KiB destination tile (+ one 16-B halo word) is
+// TMA-loaded into a shared-memory ring, 128 threads funnel-shift it from shared
+// to shared (two LDS.128 + four SHF + one STS.128 per 16 B), and the aligned
+// result is TMA-stored.  The LSU shifted path re-reads straddled sectors
+// (18.7 GB of DRAM reads for 16.06 GB, 5.98 ms); this one does not.
+constexpr int kShiftThreads = 128;
+constexpr uint32_t kShiftTile = 16u << 10;  // destination bytes per tile
+constexpr int kShiftStages = 3;             // input ring depth
+constexpr uint32_t kShiftInStride = kShiftTile + 128;  // tile + halo, 128-B aligned
+constexpr size_t kShiftSmem =
+    (size_t)kShiftStages * kShiftInStride + 2u * kShiftTile + 8u * kShiftStages;
+
+struct ShiftCursor {
+  const FcItem* items;
+  uint32_t n_items, item, voff;  // voff: vectors of the body already consumed
+  // per item (after the destination-aligning peel)
+  const uint8_t* src;  // first body byte (r = src & 15)
+  uint8_t* dst;        // 16-B aligned
+  uint32_t nvec, r;
+};
+
+template <int DIR>
+__device__ __forceinline__ void shift_fetch(ShiftCursor& c, uint8_t* arena) {
+  while (c.item < c.n_items) {
+    const uint4 a = __ldg(reinterpret_cast<const uint4*>(c.items + c.item));
+    const uint4 b = __ldg(reinterpret_cast<const uint4*>(c.items + c.item) + 1);
+    uint8_t* t = reinterpret_cast<uint8_t*>(((uint64_t)a.y << 32) | a.x);
+    uint8_t* ar = arena + (((uint64_t)a.w << 32) | a.z);
+    const uint8_t* s = DIR == 0 ? t : ar;
+    uint8_t* d = DIR == 0 ? ar : t;
+    uint32_t n = b.x;
+    uint32_t head = (uint32_t)((16u - ((uintptr_t)d & 15u)) & 15u);
+    if (head > n) head = n;
+    c.src = s + head;
+    c.dst = d + head;
+    c.nvec = (n - head) >> 4;
+    c.r = (uint32_t)((uintptr_t)c.src & 15u);
+    c.voff = 0;
+    if (c.nvec) return;
+    c.item += gridDim.x;  // nothing but peel bytes: the consumer side copies them
+  }
+}
+
+// Head (< 16 B before the aligned body) and tail (< 16 B after it) of an item.
+template <int DIR>
+__device__ __forceinline__ void shift_peel(const FcItem* items, uint32_t item, uint8_t* arena) {
+  const uint4 a = __ldg(reinterpret_cast<const uint4*>(items + item));
+  const uint4 b = __ldg(reinterpret_cast<const uint4*>(items + item) + 1);
+  uint8_t* t = reinterpret_cast<uint8_t*>(((uint64_t)a.y << 32) | a.x);
+  uint8_t* ar = arena + (((uint64_t)a.w << 32) | a.z);
+  const uint8_t* s = DIR == 0 ? t : ar;
+  uint8_t* d = DIR == 0 ? ar : t;
+  const uint32_t n = b.x;
+  uint32_t head = (uint32_t)((16u - ((uintptr_t)d & 15u)) & 15u);
+  if (head > n) head = n;
+  const uint32_t body = (n - head) & ~15u;
+  const uint32_t tail = n - head - body;
+  if (threadIdx.x < head) d[threadIdx.x] = s[threadIdx.x];
+  if (threadIdx.x >= 16 && threadIdx.x - 16 < tail) {
+    const uint32_t o = head + body + threadIdx.x - 16;
+    d[o] = s[o];
+  }
+}
+
+template <int Q>
+__device__ __forceinline__ void shift_tile(const uint8_t* in, uint8_t* out, uint32_t nv,
+                                           uint32_t sh) {
+  const uint4* __restrict__ w = reinterpret_cast<const uint4*>(in);
+  uint4* __restrict__ o = reinterpret_cast<uint4*>(out);
+  for (uint32_t i = threadIdx.x; i < nv; i += kShiftThreads) o[i] = funnel16<Q>(w[i], w[i + 1], sh);
+}
+
+template <int DIR>
+__global__ void __launch_bounds__(kShiftThreads)
+fc_copy_tma_shift(const FcItem* __restrict__ items, uint32_t n_items,
+                  uint8_t* __restrict__ arena) {
+  extern __shared__ __align__(128) uint8_t fc_smem[];
+  uint8_t* in_base = fc_smem;
+  uint8_t* out_base = fc_smem + kShiftStages * kShiftInStride;
+  const uint32_t bar_base = smem_u32(out_base + 2u * kShiftTile);
+  constexpr uint32_t kTileVec = kShiftTile / 16;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kShiftStages; ++s) mbar_init(bar_base + 8 * s, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+
+  // Peel bytes of every item this CTA owns (tiny, done up front).
+  for (uint32_t it = blockIdx.x; it < n_items; it += gridDim.x) shift_peel<DIR>(items, it, arena);
+
+  // Load cursor lives in thread 0 only; the consume cursor is replicated.
+  ShiftCursor ld, cs;
+  cs.items = items; cs.n_items = n_items; cs.item = blockIdx.x;
+  shift_fetch<DIR>(cs, arena);
+  ld = cs;
+
+  auto tile_vecs = [](const ShiftCursor& c) {
+    const uint32_t left = c.nvec - c.voff;
+    return left < kTileVec ? left : kTileVec;
+  };
+  auto advance = [&](ShiftCursor& c) {
+    c.voff += kTileVec;
+    if (c.voff >= c.nvec) {
+      c.item += gridDim.x;
+      shift_fetch<DIR>(c, arena);
+    }
+  };
+  auto issue_load = [&](uint32_t stage) {  // thread 0
+    const uint32_t nv = tile_vecs(ld);
+    const uint32_t nb = nv * 16u + (ld.r ? 16u : 0u);  // + halo word
+    const void* g = ld.src - ld.r + (size_t)ld.voff * 16u;
+    mbar_expect_tx(bar_base + 8 * stage, nb);
+    bulk_g2s(smem_u32(in_base + stage * kShiftInStride), g, nb, bar_base + 8 * stage);
+    advance(ld);
+  };
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kShiftStages && ld.item < n_items; ++s) issue_load(s);
+  }
+
+  for (uint32_t k = 0; cs.item < n_items; ++k) {
+    const uint32_t stage = k % kShiftStages;
+    mbar_wait(bar_base + 8 * stage, (k / kShiftStages) & 1u);
+    const uint32_t nv = tile_vecs(cs);
+    const uint8_t* in = in_base + stage * kShiftInStride;
+    uint8_t* out = out_base + (k & 1u) * kShiftTile;
+    const uint32_t sh = (cs.r & 3u) * 8u;
+    switch (cs.r >> 2) {
+      case 0: shift_tile<0>(in, out, nv, sh); break;
+      case 1: shift_tile<1>(in, out, nv, sh); break;
+      case 2: shift_tile<2>(in, out, nv, sh); break;
+      default: shift_tile<3>(in, out, nv, sh); break;
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // STS -> bulk store
+    __syncthreads();  // tile shifted; input stage fully read
+    if (threadIdx.x == 0) {
+      bulk_s2g(cs.dst + (size_t)cs.voff * 16u, smem_u32(out), nv * 16u);
+      bulk_commit();
+      if (ld.item < n_items) issue_load(stage);  // refill the stage just consumed
+      bulk_wait_read<1>();  // store k-1 done reading: out[(k+1)&1] is free again
+    }
+    advance(cs);
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) bulk_wait_all();
+}
+
 // ----------------------------------------------------------------- host side --
 
 struct fc_ctx {
@@ -380,6 +556,7 @@ struct fc_ctx {
   int tma_ctas_per_sm = 2;
   int tma_stages = 3;
   int tma_tile = 32 << 10;
+  int shift_ctas_per_sm = 2;
   // save pipeline state (one in flight)
   cudaEvent_t ev_pack_start = nullptr, ev_pack_end = nullptr, ev_drain_start = nullptr,
               ev_drain_end = nullptr;
@@ -468,7 +645,8 @@ struct fc_plan {
   fc_ctx* ctx = nullptr;
   FcTable all;    // every byte, <= chunk pieces (LSU variant)
   FcTable bulk;   // 16-B congruent bodies (TMA variant)
-  FcTable resid;  // heads, tails and non-congruent ranges (TMA variant)
+  FcTable resid;  // heads and tails of congruent ranges (TMA variant)
+  FcTable shift;  // ranges not congruent mod 16 (TMA variant: fc_copy_tma_shift)
   uint64_t payload = 0, arena_end = 0;
   uint32_t chunk = kDefaultChunk;
   std::vector<FcRun> runs;
@@ -770,15 +948,19 @@ static int plan_fill(fc_plan* p, uint32_t n, const void* const* dev_ptrs,
     runs.push_back(r);
   }
 
-  std::vector<FcItem> all, bulk, resid;
+  std::vector<FcItem> all, bulk, resid, shift;
   for (uint32_t i = 0; i < n; ++i) {
     uint64_t nb = nbytes[i];
     if (nb == 0) continue;
     uint64_t tp = (uint64_t)(uintptr_t)dev_ptrs[i];
     uint64_t off = arena_off[i];
     split_range(all, tp, off, nb, chunk_bytes);
-    if (((tp - off) & 15u) != 0) {  // not congruent mod 16: register-funnel path
-      split_range(resid, tp, off, nb, chunk_bytes);
+    if (((tp - off) & 15u) != 0) {  // not congruent mod 16: byte-shift path
+      // small ranges are not worth a TMA tile: leave them to the LSU kernel
+      if (nb < 4096)
+        split_range(resid, tp, off, nb, chunk_bytes);
+      else
+        split_range(shift, tp, off, nb, chunk_bytes);
       continue;
     }
     uint64_t head = std::min<uint64_t>((16u - (off & 15u)) & 15u, nb);
@@ -792,6 +974,7 @@ static int plan_fill(fc_plan* p, uint32_t n, const void* const* dev_ptrs,
   int rc = table_set(c, p->all, all, s, sync);
   if (!rc) rc = table_set(c, p->bulk, bulk, s, sync);
   if (!rc) rc = table_set(c, p->resid, resid, s, sync);
+  if (!rc) rc = table_set(c, p->shift, shift, s, sync);
   if (rc) return rc;
   p->payload = payload;
   p->arena_end = arena_end;
@@ -856,7 +1039,7 @@ extern "C" int fc_plan_destroy(fc_plan* p) {
   // the whole device) and defer the cudaFree (which would sync everything).
   if (p->ev_last_use) cudaEventSynchronize(p->ev_last_use);
   if (p->ev_upload) cudaEventSynchronize(p->ev_upload);
-  for (FcTable* t : {&p->all, &p->bulk, &p->resid}) {
+  for (FcTable* t : {&p->all, &p->bulk, &p->resid, &p->shift}) {
     if (t->dev) c->dead_dev.push_back(t->dev);
     if (t->pinned) c->dead_pinned.push_back(t->pinned);
   }
@@ -933,6 +1116,18 @@ static int launch_tma(fc_ctx* c, const FcItem* items, uint32_t n, cudaStream_t s
 }
 
 template <int DIR>
+static int launch_shift(fc_ctx* c, const FcItem* items, uint32_t n, cudaStream_t s) {
+  if (n == 0) return FC_OK;
+  FC_CUDA(cudaFuncSetAttribute(fc_copy_tma_shift<DIR>,
+                               cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kShiftSmem));
+  uint32_t grid = std::min<uint32_t>(n, (uint32_t)(c->sm_count * c->shift_ctas_per_sm));
+  fc_copy_tma_shift<DIR><<<grid, kShiftThreads, kShiftSmem, s>>>(items, n, c->arena);
+  FC_CUDA(cudaGetLastError());
+  c->n_kernels += 1;
+  return FC_OK;
+}
+
+template <int DIR>
 static int launch_copy(fc_plan* p, cudaStream_t s, int variant) {
   fc_ctx* c = p->ctx;
   if (p->arena_end > c->arena_bytes)
@@ -943,6 +1138,7 @@ static int launch_copy(fc_plan* p, cudaStream_t s, int variant) {
   int rc;
   if (variant == FC_VARIANT_TMA) {
     rc = launch_tma<DIR>(c, p->bulk.dev, p->bulk.n, s);
+    if (!rc) rc = launch_shift<DIR>(c, p->shift.dev, p->shift.n, s);
     if (!rc) rc = launch_lsu<DIR>(c, p->resid.dev, p->resid.n, s);
   } else {
     rc = launch_lsu<DIR>(c, p->all.dev, p->all.n, s);
