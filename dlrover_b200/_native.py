@@ -63,6 +63,7 @@ _SIGNATURES = {
     "fc_launch_count": (ctypes.c_int, [_vp, ctypes.POINTER(_u64), ctypes.POINTER(_u64)]),
     "fc_set_variant": (ctypes.c_int, [_vp, ctypes.c_int]),
     "fc_set_launch": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int]),
+    "fc_set_shift_launch": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int]),
     "fc_save_async": (ctypes.c_int, [_vp, _vp, _vp, ctypes.POINTER(_u64)]),
     "fc_save_pack_done": (ctypes.c_int, [_vp, _u64]),
     "fc_save_poll": (ctypes.c_int, [_vp, _u64]),
@@ -296,6 +297,10 @@ class Context:
                                          tma_stages, tma_tile_bytes),
             "fc_set_launch",
         )
+
+    def set_shift_launch(self, ctas_per_sm: int = 0, in_stages: int = 0, tile_bytes: int = 0):
+        _check(load_library().fc_set_shift_launch(self.handle, ctas_per_sm, in_stages,
+                                                  tile_bytes), "fc_set_shift_launch")
 
     def set_drain(self, piece_bytes: int = 0, depth: int = 0):
         _check(load_library().fc_set_drain(self.handle, int(piece_bytes), int(depth)),

@@ -398,12 +398,12 @@ fc_copy_tma(const FcItem* __restrict__ items, uint32_t n_items, uint8_t* __restr
 // to shared (two LDS.128 + four SHF + one STS.128 per 16 B), and the aligned
 // result is TMA-stored.  The LSU shifted path re-reads straddled sectors
 // (18.7 GB of DRAM reads for 16.06 GB, 5.98 ms); this one does not.
-constexpr int kShiftThreads = 128;
-constexpr uint32_t kShiftTile = 16u << 10;  // destination bytes per tile
-constexpr int kShiftStages = 3;             // input ring depth
-constexpr uint32_t kShiftInStride = kShiftTile + 128;  // tile + halo, 128-B aligned
-constexpr size_t kShiftSmem =
-    (size_t)kShiftStages * kShiftInStride + 2u * kShiftTile + 8u * kShiftStages;
+constexpr int kShiftThreads = 256;
+// shared memory: in_stages x (tile + 128 B halo slot) input ring, 2 x tile
+// output double buffer, in_stages mbarriers
+static inline size_t shift_smem_bytes(uint32_t tile, uint32_t in_stages) {
+  return (size_t)in_stages * (tile + 128u) + 2u * (size_t)tile + 8u * in_stages;
+}
 
 struct ShiftCursor {
   const FcItem* items;
@@ -468,14 +468,15 @@ __device__ __forceinline__ void shift_tile(const uint8_t* in, uint8_t* out, uint
 template <int DIR>
 __global__ void __launch_bounds__(kShiftThreads)
 fc_copy_tma_shift(const FcItem* __restrict__ items, uint32_t n_items,
-                  uint8_t* __restrict__ arena) {
+                  uint8_t* __restrict__ arena, uint32_t kShiftTile, uint32_t kShiftStages) {
   extern __shared__ __align__(128) uint8_t fc_smem[];
+  const uint32_t kShiftInStride = kShiftTile + 128u;
   uint8_t* in_base = fc_smem;
   uint8_t* out_base = fc_smem + kShiftStages * kShiftInStride;
   const uint32_t bar_base = smem_u32(out_base + 2u * kShiftTile);
-  constexpr uint32_t kTileVec = kShiftTile / 16;
+  const uint32_t kTileVec = kShiftTile / 16;
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kShiftStages; ++s) mbar_init(bar_base + 8 * s, 1);
+    for (uint32_t s = 0; s < kShiftStages; ++s) mbar_init(bar_base + 8 * s, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -490,7 +491,7 @@ fc_copy_tma_shift(const FcItem* __restrict__ items, uint32_t n_items,
   shift_fetch<DIR>(cs, arena);
   ld = cs;
 
-  auto tile_vecs = [](const ShiftCursor& c) {
+  auto tile_vecs = [&](const ShiftCursor& c) {
     const uint32_t left = c.nvec - c.voff;
     return left < kTileVec ? left : kTileVec;
   };
@@ -511,7 +512,7 @@ fc_copy_tma_shift(const FcItem* __restrict__ items, uint32_t n_items,
   };
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kShiftStages && ld.item < n_items; ++s) issue_load(s);
+    for (uint32_t s = 0; s < kShiftStages && ld.item < n_items; ++s) issue_load(s);
   }
 
   for (uint32_t k = 0; cs.item < n_items; ++k) {
@@ -553,10 +554,12 @@ struct fc_ctx {
   // tuning: defaults picked from the B200 sweep in profiles/r01_sweep.md
   int variant = FC_VARIANT_TMA;
   int lsu_ctas_per_sm = 2;
-  int tma_ctas_per_sm = 2;
-  int tma_stages = 3;
-  int tma_tile = 32 << 10;
+  int tma_ctas_per_sm = 1;
+  int tma_stages = 2;
+  int tma_tile = 96 << 10;
   int shift_ctas_per_sm = 2;
+  int shift_tile = 16 << 10;
+  int shift_stages = 2;
   // save pipeline state (one in flight)
   cudaEvent_t ev_pack_start = nullptr, ev_pack_end = nullptr, ev_drain_start = nullptr,
               ev_drain_end = nullptr;
@@ -1118,10 +1121,12 @@ static int launch_tma(fc_ctx* c, const FcItem* items, uint32_t n, cudaStream_t s
 template <int DIR>
 static int launch_shift(fc_ctx* c, const FcItem* items, uint32_t n, cudaStream_t s) {
   if (n == 0) return FC_OK;
+  const size_t smem = shift_smem_bytes((uint32_t)c->shift_tile, (uint32_t)c->shift_stages);
   FC_CUDA(cudaFuncSetAttribute(fc_copy_tma_shift<DIR>,
-                               cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kShiftSmem));
+                               cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   uint32_t grid = std::min<uint32_t>(n, (uint32_t)(c->sm_count * c->shift_ctas_per_sm));
-  fc_copy_tma_shift<DIR><<<grid, kShiftThreads, kShiftSmem, s>>>(items, n, c->arena);
+  fc_copy_tma_shift<DIR><<<grid, kShiftThreads, smem, s>>>(
+      items, n, c->arena, (uint32_t)c->shift_tile, (uint32_t)c->shift_stages);
   FC_CUDA(cudaGetLastError());
   c->n_kernels += 1;
   return FC_OK;
@@ -1248,6 +1253,20 @@ extern "C" int fc_save_timings(fc_ctx* c, uint64_t ticket, float* pack_ms, float
     FC_CUDA(cudaEventElapsedTime(&t, c->ev_pack_start, c->ev_drain_end));
     *total_ms = t;
   }
+  return FC_OK;
+}
+
+extern "C" int fc_set_shift_launch(fc_ctx* c, int ctas_per_sm, int in_stages, int tile_bytes) {
+  if (!c) return fail(FC_EINVAL, "fc_set_shift_launch: null ctx%s%s");
+  int cps = ctas_per_sm ? ctas_per_sm : c->shift_ctas_per_sm;
+  int st = in_stages ? in_stages : c->shift_stages;
+  int tile = tile_bytes ? tile_bytes : c->shift_tile;
+  if (cps < 1 || cps > 8 || st < 2 || st > 8 || tile < 4096 || (tile & 127) ||
+      shift_smem_bytes((uint32_t)tile, (uint32_t)st) > (227u << 10))
+    return fail(FC_EINVAL, "fc_set_shift_launch: out of range%s%s");
+  c->shift_ctas_per_sm = cps;
+  c->shift_stages = st;
+  c->shift_tile = tile;
   return FC_OK;
 }
 

@@ -127,6 +127,9 @@ int fc_set_variant(fc_ctx* ctx, int variant);
 int fc_set_launch(fc_ctx* ctx, int lsu_ctas_per_sm, int tma_ctas_per_sm,
                   int tma_stages, int tma_tile_bytes);
 
+/* same for the byte-shift kernel (ranges not congruent mod 16) */
+int fc_set_shift_launch(fc_ctx* ctx, int ctas_per_sm, int in_stages, int tile_bytes);
+
 /* ---- save: snapshot + drain ---------------------------------------------- */
 
 /* Enqueue the pack kernel on `compute_stream` (the ONLY work the training

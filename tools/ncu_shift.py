@@ -42,3 +42,20 @@ if os.getenv("SWEEP"):
         b.record()
         torch.cuda.synchronize()
         print("ctas/sm", cps, "ms", round(a.elapsed_time(b) / 5, 3))
+
+if os.getenv("SWEEP_SHIFT"):
+    for cps, st, tile in ((2, 3, 16), (2, 2, 24), (1, 2, 32), (1, 2, 48), (1, 3, 32), (1, 2, 56),
+                          (2, 2, 16), (1, 4, 24), (3, 2, 16), (1, 2, 40)):
+        try:
+            ctx.set_shift_launch(cps, st, tile << 10)
+        except native.NativeError as e:
+            print("skip", cps, st, tile, e)
+            continue
+        for _ in range(2):
+            plan.pack(s, native.VARIANT_AUTO)
+        a.record()
+        for _ in range(5):
+            plan.pack(s, native.VARIANT_AUTO)
+        b.record()
+        torch.cuda.synchronize()
+        print("shiftcfg ctas", cps, "stages", st, "tileK", tile, "ms", round(a.elapsed_time(b) / 5, 3))
