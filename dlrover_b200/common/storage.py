@@ -71,12 +71,44 @@ class CheckpointStorage(metaclass=ABCMeta):
         """ClassMeta from which another process can rebuild this storage."""
 
 
+def _parallel_write(path: str, view: memoryview, threads: int, piece: int = 64 << 20):
+    """Write a large buffer with `threads` concurrent pwrite() streams (each call
+    releases the GIL); same bytes, same file, fsync'd once at the end."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    view = view.cast("B")
+    total = view.nbytes
+    fd = os.open(path, os.O_WRONLY | os.O_CREAT | os.O_TRUNC, 0o644)
+    try:
+        os.ftruncate(fd, total)
+
+        def put(off):
+            end = min(total, off + piece)
+            while off < end:
+                off += os.pwrite(fd, view[off:end], off)
+
+        with ThreadPoolExecutor(max_workers=threads) as pool:
+            list(pool.map(put, range(0, total, piece)))
+        os.fsync(fd)
+    finally:
+        os.close(fd)
+
+
 class PosixDiskStorage(CheckpointStorage):
-    """Local / NFS-like file system; every write is fsync'd before returning."""
+    """Local / NFS-like file system; every write is fsync'd before returning.
+    Buffers >= 256 MiB (the raw shm segment of the FSDP/DCP saver) are written
+    by several pwrite streams."""
+
+    PARALLEL_WRITE_MIN = 256 << 20
+    PARALLEL_WRITE_THREADS = max(1, min(8, (os.cpu_count() or 1) // 2))
 
     def write(self, content, path):
         binary = isinstance(content, (bytes, bytearray, memoryview))
         try:
+            if binary and self.PARALLEL_WRITE_THREADS > 1 and \
+                    memoryview(content).nbytes >= self.PARALLEL_WRITE_MIN:
+                _parallel_write(str(path), memoryview(content), self.PARALLEL_WRITE_THREADS)
+                return
             with open(path, "wb" if binary else "w") as f:
                 f.write(content)
                 f.flush()

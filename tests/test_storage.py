@@ -76,3 +76,18 @@ def test_class_meta_round_trip(tmp_path):
     clone = meta.instantiate()
     assert isinstance(clone, PosixStorageWithDeletion) and clone._tracker_file == "dlrover_latest.txt"
     assert isinstance(get_checkpoint_storage(None), PosixDiskStorage)
+
+
+def test_parallel_write_is_byte_identical(tmp_path, monkeypatch):
+    import numpy as np
+
+    st = PosixDiskStorage()
+    monkeypatch.setattr(PosixDiskStorage, "PARALLEL_WRITE_MIN", 1 << 20)
+    monkeypatch.setattr(PosixDiskStorage, "PARALLEL_WRITE_THREADS", 4)
+    data = np.random.default_rng(0).integers(0, 256, size=(70 << 20) + 12345, dtype=np.uint8)
+    p = str(tmp_path / "seg.distcp")
+    st.write(memoryview(data), p)
+    assert os.path.getsize(p) == data.size
+    assert np.array_equal(np.fromfile(p, dtype=np.uint8), data)
+    st.write(memoryview(data[:100]), p)  # small again: plain path, truncates
+    assert os.path.getsize(p) == 100
