@@ -636,6 +636,10 @@ class MegatronCheckpointEngine(_ShardedRanksMixin, _MegatronTopology, Checkpoint
     @timer
     def save_to_storage(self, step, state_dict, paths):
         succeed = self._memory_then_barrier(step, state_dict, paths)
+        if succeed:
+            # (the reference forgets this, so its wait_latest_checkpoint on a
+            # Megatron engine always runs into the timeout)
+            self.latest_step = step
         # one notifier per node: dp rank 0's local rank 0
         if self._dp_rank != 0 or self._local_rank != 0:
             return

@@ -247,13 +247,41 @@ class SharedMemoryReader(StorageReader):
         self.shm_handler = shm_handler
         self.state_dict_metadata: Dict[str, STORAGE_TYPES] = {}
         self.no_shard_data: Dict[str, STORAGE_TYPES] = {}
+        self.last_fast_items = 0  # items of the last read_data served by DMA + scatter
+
+    def _device_fast_path(self, read_item: ReadItem, info: _StorageInfo, planner: LoadPlanner):
+        """(target, offset, nbytes) when the item is a whole stored chunk going
+        into a contiguous CUDA tensor of the same dtype — then it joins the
+        one-shot DMA + scatter instead of a per-item pageable H2D copy_
+        (reference fsdp_engine.py:303)."""
+        if read_item.type == LoadItemType.BYTE_IO or not read_item.storage_index.offset:
+            return None
+        md = self.state_dict_metadata.get(read_item.storage_index.fqn)
+        if not isinstance(md, TensorStorageMetadata):
+            return None
+        if any(int(o) != 0 for o in read_item.storage_offsets):
+            return None
+        if tuple(_chunk_shape(md, read_item)) != tuple(read_item.lengths):
+            return None
+        target = planner.resolve_tensor(read_item).detach()
+        if not (target.is_cuda and target.is_contiguous()) or \
+                target.dtype != md.properties.dtype or \
+                target.numel() * target.element_size() != info.length or \
+                tuple(target.size()) != tuple(read_item.lengths):
+            return None
+        return target, info.offset, info.length
 
     def read_data(self, plan: LoadPlan, planner: LoadPlanner) -> Future[None]:
         self.shm_handler.wait_pending()
         if self.shm_handler.shared_memory is None:
             self.shm_handler.init_shared_memory()
+        fast = []  # (read_item, target, offset, nbytes)
         for read_item in plan.items:
             info = self.storage_data[read_item.storage_index]
+            hit = self._device_fast_path(read_item, info, planner)
+            if hit is not None:
+                fast.append((read_item,) + hit)
+                continue
             pickled = False
             if not read_item.storage_index.offset:
                 # non-sharded entry: taken from the broadcast copy, not the segment
@@ -273,6 +301,11 @@ class SharedMemoryReader(StorageReader):
             if read_item.type != LoadItemType.BYTE_IO:
                 md = self.state_dict_metadata[read_item.storage_index.fqn]
             _load_item(read_item, item_bytes, planner, md, pickled=pickled)
+        self.last_fast_items = len(fast)
+        if fast:
+            self.shm_handler.read_ranges([(t, off, n) for _, t, off, n in fast])
+            for read_item, target, _, _ in fast:
+                planner.commit_tensor(read_item, target)
         fut: Future = Future()
         fut.set_result(None)
         return fut

@@ -577,6 +577,32 @@ class SharedMemoryHandler:
                 stats["device_bytes"] = float(plan.payload_bytes)
         return stats
 
+    def read_ranges(self, device_ranges, stream=None) -> Dict[str, float]:
+        """Inverse of write_ranges for CUDA targets: (tensor, segment offset,
+        nbytes) triples are filled by one DMA of the covered segment runs into
+        the arena + one scatter kernel into the (contiguous) tensors."""
+        self.wait_pending()
+        if not device_ranges:
+            return {"device_bytes": 0.0, "fill_ms": 0.0, "scatter_ms": 0.0}
+        if self.shared_memory is None or self._need_creation:
+            self.init_shared_memory(create=False)
+        if not self.shared_memory:
+            raise RuntimeError("the checkpoint segment does not exist")
+        for t, off, nbytes in device_ranges:
+            if not (t.is_cuda and t.is_contiguous()):
+                raise ValueError("read_ranges needs contiguous CUDA targets")
+            if off + nbytes > self.shared_memory.size or t.numel() * t.element_size() != nbytes:
+                raise ValueError("read_ranges: range does not fit the segment / the tensor")
+        stager = self._stager_for([r[0] for r in device_ranges])
+        stager.attach(self.shared_memory)
+        if stream is None:
+            stream = torch.cuda.current_stream(stager.device_index)
+        plan = stager.plan_for(device_ranges, [], role="restore", stream=stream)
+        plan.restore_async(self.shared_memory.address, stream)
+        stager.ctx.restore_wait()
+        fill, scatter, _ = stager.ctx.restore_timings()
+        return {"device_bytes": float(plan.payload_bytes), "fill_ms": fill, "scatter_ms": scatter}
+
     # -- queries ------------------------------------------------------------------------
     def no_checkpoint_state(self):
         """True when the meta dict holds no config or step 0.  (The agent-side

@@ -127,6 +127,8 @@ def _engine_roundtrip(tmp_path, device, async_drain):
     reader = engine.load()
     assert isinstance(reader, fe.SharedMemoryReader)
     dist_cp.load(target, storage_reader=reader)
+    if device == "cuda":
+        assert reader.last_fast_items == 3  # all tensors via one DMA fill + scatter kernel
     assert torch.equal(target["model"]["w"], sd["model"]["w"])
     assert torch.equal(target["model"]["b"], sd["model"]["b"])
     assert torch.equal(target["optim"]["m"], sd["optim"]["m"])

@@ -59,7 +59,11 @@ def _worker(rank, world, port, run_id, ckpt_dir, mode, out_dir):
             sd = {"w": torch.arange(100, dtype=torch.float32)}
             ckpt.save_checkpoint(7, sd, storage_type=StorageType.DISK)
             result["cached_step"] = eng._cached_step
-            ckpt.wait_latest_checkpoint(timeout=90)
+            # only a saving rank tracks latest_step; the others would poll
+            # until the timeout (same in the reference)
+            if rank == 0:
+                ckpt.wait_latest_checkpoint(timeout=90)
+            dist.barrier()
             result["files"] = sorted(os.listdir(os.path.join(ckpt_dir, "7")))
             # rank 1 never wrote memory: steps differ across ranks, so nobody
             # restores from memory and both fall back to rank 0's file
