@@ -555,6 +555,9 @@ def _hf_safetensors_target(state_name: str, path: str):
     if re.fullmatch(r"(.*?)-\d{5}-of-\d{5}.bin", state_name):
         return (path.replace("pytorch_model", "model").replace(".bin", ".safetensors"),
                 safe_save_file)
+    if state_name.endswith(".safetensors"):
+        # recorded from transformers' own safetensors writer (hf_trainer.py)
+        return path, lambda sd, p: safe_save_file(sd, p, metadata={"format": "pt"})
     return path, torch.save
 
 

@@ -61,6 +61,7 @@ class AsyncCheckpointAgent:
     def __init__(self, storage: CheckpointStorage):
         self.state_dict: Dict[str, object] = {}
         self.paths: Dict[str, str] = {}
+        self.safetensors_metadata: Dict[str, object] = {}
         self.storage = storage
 
     def create(self, tag):

@@ -253,3 +253,30 @@ def test_megatron_deletion_strategies(tmp_path):
     interval.clean_up(200, shutil.rmtree)
     assert not os.path.exists(tmp_path / "iter_0000100")
     assert isinstance(fc_dist.get_checkpoint_storage(keep), fc_dist.PosixStorageWithDeletion)
+
+
+def test_hf_checkpointer_records_and_persists(agent, tmp_path):
+    """The part of the HF adapter that does not need a live Trainer: entries
+    recorded from torch.save / safetensors are persisted under their paths."""
+    from dlrover_b200.flash_checkpoint.hf_trainer import HfDdpCheckpointer, _SafetensorsRecorder
+
+    ckpt = HfDdpCheckpointer(str(tmp_path))
+    agent_ = ckpt.ckpt_agent
+    agent_.safetensors_metadata = {}
+    out = tmp_path / "checkpoint-2"
+    os.makedirs(out)
+    model = SimpleNet()
+    _SafetensorsRecorder(agent_)(dict(model.state_dict()), str(out / "model.safetensors"),
+                                 metadata={"format": "pt"})
+    agent_.save({"state": {}, "param_groups": [{"lr": 0.1}]}, str(out / "optimizer.pt"))
+    agent_.save({"python": 1}, str(out / "rng_state.pth"))
+    assert ckpt.save_checkpoint_to_storage(2)
+    ckpt.async_save_engine.wait_latest_checkpoint(timeout=60)
+    assert sorted(os.listdir(out)) == ["model.safetensors", "optimizer.pt", "rng_state.pth"]
+    from safetensors.torch import load_file
+
+    back = load_file(str(out / "model.safetensors"))
+    want = model.state_dict()
+    assert set(back) == set(want) and all(torch.equal(back[k], want[k]) for k in want)
+    assert torch.load(out / "optimizer.pt", weights_only=False)["param_groups"][0]["lr"] == 0.1
+    ckpt.async_save_engine.close()
