@@ -405,10 +405,19 @@ def measure_stall(ckpt, sd, S, dev, world):
     b = torch.randn(8192, 8192, device=dev, dtype=torch.bfloat16) * 0.01
     inner, rounds = 40, 6
 
+    grad = torch.zeros(4 << 20, device=dev) if world > 1 else None
+
     def train_step():
         c = a
         for _ in range(inner):
             c = torch.mm(c, b)
+        if grad is not None:
+            # DDP-style gradient all-reduce: keeps the ranks in lockstep like a
+            # real data-parallel step does (without it they drift apart and the
+            # checkpoint's readiness collective measures that drift)
+            import torch.distributed as dist
+
+            dist.all_reduce(grad)
         # like `loss.item()` in a real loop: the host does not run ahead of
         # the device by more than one step
         return float(c[0, 0].item())

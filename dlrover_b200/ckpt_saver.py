@@ -531,10 +531,23 @@ class CommonDirCheckpointSaver(AsyncCheckpointSaver):
             if not sd or state_name not in ckpt_config.paths:
                 continue
             path = ckpt_config.paths[state_name]
-            writer = torch.save
+            # same bytes as torch.save, written and CRC'd by several threads
+            writer = _torch_save_writer()
             if safe_serialization:
                 path, writer = _hf_safetensors_target(state_name, path)
             self.storage.write_state_dict(sd, path, writer)
+
+
+def _torch_save_writer():
+    """`write_func(state_dict, path)` producing exactly torch.save's file.
+    DLROVER_B200_FAST_PERSIST=0 selects plain torch.save."""
+    if os.getenv("DLROVER_B200_FAST_PERSIST", "1") in ("0", "false", "False"):
+        return torch.save
+    from . import fast_torch_save
+
+    threads = int(os.getenv("DLROVER_B200_PERSIST_THREADS", "0") or 0) or \
+        max(1, min(16, (os.cpu_count() or 1) // 2))
+    return lambda sd, path: fast_torch_save.save(sd, path, threads=threads)
 
 
 def _hf_safetensors_target(state_name: str, path: str):
@@ -558,7 +571,7 @@ def _hf_safetensors_target(state_name: str, path: str):
     if state_name.endswith(".safetensors"):
         # recorded from transformers' own safetensors writer (hf_trainer.py)
         return path, lambda sd, p: safe_save_file(sd, p, metadata={"format": "pt"})
-    return path, torch.save
+    return path, _torch_save_writer()
 
 
 class TempDirCheckpointSaver(AsyncCheckpointSaver):
