@@ -235,6 +235,9 @@ def run_ours(args):
     rank, local, world = dist_env()
     os.environ.setdefault("TORCHELASTIC_RUN_ID", f"fcbench{os.getppid()}")
     os.environ.setdefault("DLROVER_LOG_LEVEL", "WARNING")
+    # NCCL prints "NCCL version ..." to STDOUT at NCCL_DEBUG>=VERSION; stdout is
+    # reserved for the one JSON line
+    os.environ["NCCL_DEBUG"] = os.getenv("BENCH_NCCL_DEBUG", "NONE")
     import torch
     import torch.distributed as dist
 

@@ -123,7 +123,7 @@ def _zip64_extra(usize=None, csize=None, offset=None) -> bytes:
     return struct.pack("<HH", 0x0001, len(body)) + body
 
 
-def fast_save(obj, path: str, threads: int = 8, pickle_protocol: int = 2) -> None:
+def fast_save(obj, path: str, threads: int = 4, pickle_protocol: int = 2) -> None:
     """Write `obj` to `path` exactly as torch.save(obj, path) would."""
     path = os.fspath(path)
     prefix = os.path.splitext(os.path.basename(path))[0]
@@ -220,13 +220,14 @@ def fast_save(obj, path: str, threads: int = 8, pickle_protocol: int = 2) -> Non
                     off += os.pwrite(fd, view[off:stop], base + off)
 
             list(pool.map(put, jobs))
-            os.fsync(fd)
+            # no fsync: torch.save does not sync either (the reference only
+            # fsyncs its small tracker/done files, storage.py:129-141)
         finally:
             os.close(fd)
     del rec
 
 
-def save(obj, path, threads: int = 8):
+def save(obj, path, threads: int = 4):
     """fast_save with a torch.save fallback (same bytes either way)."""
     try:
         fast_save(obj, path, threads=threads)
