@@ -245,8 +245,9 @@ class LocalSocketComm:
                     _send_frame(conn, pickle.dumps(response))
                 except (ConnectionError, OSError):
                     break
-                if not self._persist:
-                    break
+                # keep serving this connection until the peer closes it: one-shot
+                # clients (the reference's queue/dict clients) close right after
+                # the reply, persistent ones save a connect + thread per request
         finally:
             self._on_disconnect(held)
             try:
@@ -270,6 +271,7 @@ class LocalSocketComm:
         payload = pickle.dumps(request)
         with self._client_mutex:
             attempt = 0
+            stale_retry = self._persist and self._client is not None
             while True:
                 try:
                     if self._client is None:
@@ -291,6 +293,14 @@ class LocalSocketComm:
                     if attempt > retry:
                         raise
                     time.sleep(1)
+                except (EOFError, BrokenPipeError, ConnectionResetError):
+                    # a kept connection the owner has closed meanwhile (owner
+                    # restarted, or it serves one request per connection):
+                    # reconnect once
+                    self._drop_client()
+                    if not stale_retry:
+                        raise
+                    stale_retry = False
                 except Exception:
                     self._drop_client()
                     raise
@@ -386,6 +396,8 @@ class SharedLock(LocalSocketComm):
 class SharedQueue(LocalSocketComm):
     """A FIFO shared by name; the owner holds a ``queue.Queue(maxsize)``."""
 
+    _persistent = True  # client keeps one connection (see LocalSocketComm._serve)
+
     def __init__(self, name: str = "", create: bool = False, maxsize: int = 1):
         self._queue = queue.Queue(maxsize) if create else None
         super().__init__(name, create)
@@ -444,6 +456,8 @@ class SharedDict(LocalSocketComm):
     it never returns a dict older than a set already under way
     (reference multi_process.py:594-597, :614-616, :663-666).
     """
+
+    _persistent = True
 
     def __init__(self, name: str = "", create: bool = False):
         self._dict: Any = {}
