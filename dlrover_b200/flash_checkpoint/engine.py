@@ -295,6 +295,18 @@ class CheckpointEngine(metaclass=ABCMeta):
             return self._local_rank == self.local_shard_id
         return not self._saving_ranks or self._rank in self._saving_ranks
 
+    # Optional: a CUDA stream for the gather kernel (default: the current one).
+    # With a side stream the snapshot overlaps the next forward/backward (which
+    # only read the parameters); the caller must then order its next MUTATION of
+    # the saved tensors after the snapshot:
+    #     torch.cuda.current_stream().wait_event(engine.pack_done_event())
+    # right before optimizer.step().
+    snapshot_stream = None
+
+    def pack_done_event(self):
+        """torch.cuda.Event recorded after the gather kernel of the last save."""
+        return self._shm_handler.last_pack_event
+
     def save_state_dict_to_memory(self, state_dict, conf: CheckpointConfig, blocking=False):
         """Returns True when the state dict was (or is being) written to shared
         memory, False when this rank does not save or the save was skipped."""
@@ -332,7 +344,8 @@ class CheckpointEngine(metaclass=ABCMeta):
         try:
             # replica backup issues collectives: keep those on the calling thread
             sync = not self._async_drain or self._replica_manager.has_replica()
-            self._shm_handler.save_state_dict(state_dict, blocking=sync, on_complete=completed)
+            self._shm_handler.save_state_dict(state_dict, blocking=sync, on_complete=completed,
+                                              stream=self.snapshot_stream)
         except BaseException:
             if acquired and self._shm_handler.pending_save() is None:
                 self._shm_lock.release()

@@ -310,6 +310,8 @@ class SharedMemoryHandler:
         self._pending: Optional[PendingSave] = None
         self._master_client = None
         self.last_timings: Optional[Tuple[float, float, float]] = None
+        # torch.cuda.Event recorded right after the last gather kernel
+        self.last_pack_event = None
 
     # -- lifecycle ------------------------------------------------------------------
     def close(self):
@@ -417,10 +419,19 @@ class SharedMemoryHandler:
         if device_ranges:
             stager = self._stager_for([r[0] for r in device_ranges])
             stager.attach(self.shared_memory)
+            current = torch.cuda.current_stream(stager.device_index)
             if stream is None:
-                stream = torch.cuda.current_stream(stager.device_index)
+                stream = current
+            elif stream != current:
+                # snapshot on a side stream: it must see everything the training
+                # stream has enqueued so far, and the caller must make the training
+                # stream wait for `last_pack_event` before it MUTATES the tensors
+                stream.wait_stream(current)
             plan = stager.plan_for(device_ranges, keepalive, role="save", stream=stream)
             ticket = plan.save_async(self.shared_memory.address, stream)
+            ev = torch.cuda.Event()
+            ev.record(stream)
+            self.last_pack_event = ev
             ctx = stager.ctx
         pending = PendingSave(ctx, ticket, finish or (lambda: None), keepalive)
         self._pending = pending

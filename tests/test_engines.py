@@ -245,3 +245,21 @@ def test_megatron_engines(agent, tmp_path):
     assert dist_engine.save_to_memory(30, {MODEL: sd}, {MODEL: path})
     assert dist_engine.load()[0] == 30
     dist_engine.close()
+
+
+@pytest.mark.gpu
+def test_snapshot_on_a_side_stream(cuda_device, agent, tmp_path):
+    """Gather kernel on a side stream: it still sees everything enqueued on the
+    training stream before the call, and pack_done_event() orders the next
+    mutation after it."""
+    engine = FullCheckpointEngine(str(tmp_path), PosixDiskStorage(), async_drain=True)
+    engine.snapshot_stream = torch.cuda.Stream()
+    w = torch.zeros(64 << 20, dtype=torch.float32, device=cuda_device)  # 256 MB
+    w.fill_(3.0)  # enqueued on the training stream right before the save
+    assert engine.save_to_memory(1, {MODEL: {"w": w}}, {MODEL: str(tmp_path / "x.pt")})
+    torch.cuda.current_stream().wait_event(engine.pack_done_event())
+    w.fill_(7.0)  # the "optimizer step"
+    assert engine.wait_memory_save(120)
+    saved = engine.load()["w"]
+    assert float(saved.min()) == 3.0 and float(saved.max()) == 3.0
+    engine.close()

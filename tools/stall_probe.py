@@ -43,6 +43,9 @@ def step():
     torch.cuda.current_stream().synchronize()
 
 
+overlap = os.getenv("PROBE_OVERLAP") == "1"
+if overlap:
+    ckpt.engine.snapshot_stream = torch.cuda.Stream()
 ckpt.save_checkpoint(1, sd, storage_type=StorageType.MEMORY)
 ckpt.wait_memory_save()
 for _ in range(5):
@@ -52,6 +55,9 @@ for i in range(60):
     t0 = time.perf_counter()
     step()
     t1 = time.perf_counter()
+    if overlap and i % 20 == 11:
+        # "optimizer.step()" of the step after the checkpoint: first mutation
+        torch.cuda.current_stream().wait_event(ckpt.engine.pack_done_event())
     if i % 20 == 10:
         ckpt.save_checkpoint(100 + i, sd, storage_type=StorageType.MEMORY)
         marks.append(i)
@@ -59,7 +65,7 @@ for i in range(60):
     times.append((round((t1 - t0) * 1e3, 1), round((t2 - t1) * 1e3, 1)))
 ckpt.wait_memory_save()
 if rank == 0:
-    print(json.dumps({"world": world, "sync": mode, "noready": os.getenv("PROBE_NOREADY"),
+    print(json.dumps({"world": world, "sync": mode, "overlap": overlap, "noready": os.getenv("PROBE_NOREADY"),
                       "save_at": marks, "step_ms,save_call_ms": times}), flush=True)
 if world > 1:
     dist.barrier()
