@@ -133,6 +133,9 @@ class ShardCkptReplicaManager(CkptReplicaManger):
         for rank in self.backup_ranks:
             if rank == self.rank:
                 holders[rank] = shm_handler
+            elif rank in self._rank_shms:
+                # the copy (and its meta dict) this process received in backup()
+                holders[rank] = self._rank_shms[rank]
             else:
                 h = SharedMemoryHandler(local_rank=rank)
                 h.init_shared_memory()

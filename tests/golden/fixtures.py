@@ -122,6 +122,18 @@ def fixture_llama_tiny():
     return {"model": sd}
 
 
+def fixture_dcp():
+    """State dict for the DCP/FSDP engine golden: nested dicts of tensors (odd
+    sizes, several dtypes) + non-tensor leaves (pickled by DCP as BYTE_IO)."""
+    return {
+        "model": {"w": pat((33, 17), torch.float32, 60), "b": pat((17,), torch.bfloat16, 61),
+                  "emb": pat((50, 8), torch.float16, 62)},
+        "optim": {"m": pat((33, 17), torch.float32, 63), "count": pat((3,), torch.int64, 64)},
+        "step": 42,
+        "name": "golden",
+    }
+
+
 FIXTURES = {
     "simplenet_sgd": fixture_simplenet_sgd,
     "toymodel_adam": fixture_toymodel_adam,

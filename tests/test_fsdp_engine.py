@@ -166,3 +166,49 @@ def test_load_without_memory_or_files_returns_none(gloo, tmp_path):
     assert engine.load() is None
     assert engine._get_track_resume_path() == ""
     engine.close()
+
+
+def _against_reference_golden(tmp_path, device, async_drain):
+    """Segment image, per-item (fqn, offset, length) table and target path must
+    equal what the REFERENCE's FsdpCheckpointEngine produced for the same state
+    dict (tests/golden/make_golden_fsdp.py -> dcp_plain.*)."""
+    import hashlib
+    import json
+    import sys
+
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+    import fixtures
+    from tests.util import GOLDEN, to_device
+
+    info = json.load(open(os.path.join(GOLDEN, "dcp_plain.json")))
+    if torch.__version__ != info["torch_version"]:
+        pytest.skip("DCP plans / pickled BYTE_IO items are torch-version specific")
+    want = np.fromfile(os.path.join(GOLDEN, "dcp_plain.bin"), dtype=np.uint8)
+    engine = fe.FsdpCheckpointEngine(str(tmp_path), PosixDiskStorage(), async_drain=async_drain)
+    sd = to_device(fixtures.fixture_dcp(), device)
+    assert engine.save_to_memory(7, sd, {"model_states": str(tmp_path / "7")})
+    engine.wait_memory_save()
+    time.sleep(0.3)
+    got = np.frombuffer(engine._shm_handler.shared_memory.buf, dtype=np.uint8)
+    assert got.size == info["size"]
+    assert np.array_equal(got, want)
+    assert hashlib.sha256(got.tobytes()).hexdigest() == info["sha256"]
+    meta = engine._shm_handler.metadata.get()
+    items = sorted([idx.fqn, list(idx.offset) if idx.offset is not None else None,
+                    si.relative_path, si.offset, si.length]
+                   for idx, si in meta["dcp_metadata"].storage_data.items())
+    assert items == info["items"]
+    assert sorted(meta["no_shard_data"].keys()) == info["no_shard_keys"]
+    conf = meta[DLROVER_CKPT_CONFIG_KEY]
+    assert os.path.relpath(conf.paths["model_states"], str(tmp_path)) == info["path"]
+    del got
+    engine.close()
+
+
+def test_segment_equals_reference_fsdp_engine_cpu(gloo, tmp_path):
+    _against_reference_golden(tmp_path, "cpu", async_drain=False)
+
+
+@pytest.mark.gpu
+def test_segment_equals_reference_fsdp_engine_cuda(cuda_device, gloo, tmp_path):
+    _against_reference_golden(tmp_path, "cuda", async_drain=True)
