@@ -351,6 +351,9 @@ def run_ours(args):
     e2e = S * world * args.steps / e2e_ms / 1e6
     api_timings = ckpt.engine.last_save_timings()
 
+    # ---- leg 2b: restore from memory (metric iv of SURVEY §8d) ---------------------------
+    restore = measure_restore(ckpt, sd, S, world)
+
     # ---- leg 3: exposed stall with a synthetic training step ----------------------------
     stall = None
     if not args.no_stall:
@@ -377,6 +380,7 @@ def run_ours(args):
                     "note": "inputs of this path are the live device-resident parameters; "
                             "the host buffer is the shm segment the drain fills"},
             "stall_ms": stall,
+            "restore": restore,
             "roofline": {"bound": "hbm", "kernel": "fc_copy_tma<0> (gather/pack)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": ncu_traffic(),
@@ -479,6 +483,38 @@ def measure_stall(ckpt, sd, S, dev, world):
                   "(returns after enqueueing the gather kernel), 'blocking' = waits for the "
                   "drain inside the step like the reference",
     }
+
+
+def measure_restore(ckpt, sd, S, world):
+    """In-memory restore of the shard: ours = DMA fill of the arena + scatter
+    kernel into the live tensors (load_checkpoint_into); reference style =
+    load_checkpoint() (CPU views on the segment) + per-tensor copy_ to the
+    device, which is what model.load_state_dict does."""
+    import torch
+
+    keys = list(sd)
+    probe = [sd[k].clone() for k in (keys[0], keys[7], keys[-1])]
+    for t in sd.values():
+        t.zero_()
+    barrier_sync(world)
+    t0 = time.perf_counter()
+    step = ckpt.load_checkpoint_into(sd)
+    torch.cuda.synchronize()
+    ours = time.perf_counter() - t0
+    ok = step > 0 and all(torch.equal(sd[k], p) for k, p in zip((keys[0], keys[7], keys[-1]), probe))
+    out = {"ours_ms": ours * 1e3, "ours_GBps": S / ours / 1e9, "bit_exact_spot_check": bool(ok)}
+    if world == 1:
+        barrier_sync(world)
+        t0 = time.perf_counter()
+        loaded = ckpt.load_checkpoint()
+        with torch.no_grad():
+            for k, t in sd.items():
+                t.copy_(loaded[k])
+        torch.cuda.synchronize()
+        ref = time.perf_counter() - t0
+        del loaded
+        out.update({"reference_style_ms": ref * 1e3, "reference_style_GBps": S / ref / 1e9})
+    return out
 
 
 def measure_cpu_baseline(sd, S):

@@ -318,6 +318,13 @@ class AsyncCheckpointSaver(metaclass=ABCMeta):
                 logger.error(f"The step {step} in event is no equal to step {config.step} "
                              "in memory.")
                 return False
+            if config.writing_shm:
+                # the trainer died (its lock was dropped with its connection)
+                # while filling the segment: the bytes are not a checkpoint.  The
+                # reference persists nothing here but still commits the step.
+                logger.error(f"Shard {local_shard_id} of step {step} is only partly written "
+                             "(writing_shm is set): not persisting it.")
+                return False
             logger.info(f"Saves the checkpoint shard {local_shard_id} of rank "
                         f"{ckpt_config.rank} from the shared memory into the storage "
                         f"{ckpt_config}.")

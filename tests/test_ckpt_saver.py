@@ -329,3 +329,21 @@ def test_failing_persist_releases_lock_and_reports(run_env, tmp_path):
     saver._report_failure_to_master("boom")
     assert reported and "boom" in reported[0][0]
     saver.close()
+
+
+def test_half_written_segment_is_never_committed(run_env, tmp_path):
+    """A trainer that dies while filling/draining leaves writing_shm=True and
+    (through its dropped connection) a free lock: the agent must neither persist
+    nor commit that step."""
+    saver = DdpCheckpointSaver(str(tmp_path), _storage_meta())
+    _fill(saver, 0, 5, str(tmp_path / "5" / "rank_0.pt"))
+    meta = saver._shm_handlers[0].metadata.get()
+    meta[DLROVER_CKPT_CONFIG_KEY].writing_shm = True
+    saver._shm_handlers[0].metadata.set(meta)
+    saver.save_step_checkpoint(5)
+    assert not (tmp_path / "dlrover_latest.txt").exists()
+    assert not (tmp_path / "5").exists()
+    assert saver._latest_step == 0 and not saver._any_rank_locked()
+    saver.save_shm_to_storage()  # breakpoint save: same answer
+    assert not (tmp_path / "dlrover_latest.txt").exists()
+    saver.close()
