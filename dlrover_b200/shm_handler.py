@@ -218,7 +218,7 @@ class _DeviceStager:
             if not t.is_contiguous():
                 # rare (state_dict tensors are contiguous); device-side repack,
                 # kept alive until the pack kernel has consumed it
-                t = t.contiguous()
+                t = t.detach().contiguous()
                 keepalive.append(t)
             ptrs.append(t.data_ptr())
             offs.append(off)
