@@ -192,6 +192,19 @@ def run_reference(args):
             saver.save(sd)
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
+        # restore the reference's way: CPU views on the (pageable) segment, one
+        # H2D copy_ per tensor (ckpt_saver.py:144-161 + model.load_state_dict)
+        from oracle import shm_layout
+
+        views = shm_layout_read(saver)
+        torch.cuda.synchronize()
+        r0 = time.perf_counter()
+        with torch.no_grad():
+            for k, t in sd["model_states"].items():
+                t.copy_(views["model_states"][k])
+        torch.cuda.synchronize()
+        restore_s = time.perf_counter() - r0
+        del views
     finally:
         clk = clocks.stop()
         saver.close()
@@ -204,6 +217,8 @@ def run_reference(args):
         "config": workload_config(S, 1, args.scale),
         "stall_ms": {"blocking": dt / args.steps * 1e3,
                      "note": "the reference blocks the training thread for the whole copy"},
+        "restore": {"reference_ms": restore_s * 1e3, "reference_GBps": S / restore_s / 1e9,
+                    "how": "frombuffer views on the pageable segment + per-tensor copy_ to cuda"},
         "cpu_baseline": {"value": gbs, "unit": UNIT, "cores": 1, "kind": "port",
                          "host_cores": os.cpu_count(),
                          "sample": f"{args.steps} full saves of the {S / 1e9:.2f} GB state_dict: "
@@ -214,6 +229,23 @@ def run_reference(args):
     }
     print(json.dumps(line), flush=True)
     return 0
+
+
+def shm_layout_read(saver):
+    """Tensors aliasing the reference-port segment (ckpt_saver.py:144-161)."""
+    import torch
+
+    from oracle.shm_layout import OracleTensorMeta, traverse
+
+    def visit(m):
+        if isinstance(m, OracleTensorMeta):
+            if m.numel == 0:
+                return torch.tensor([], dtype=m.dtype)
+            return torch.frombuffer(saver.segment.buf, dtype=m.dtype, offset=m.offset,
+                                    count=m.numel).reshape(m.shape)
+        return m
+
+    return traverse(saver.meta, visit)
 
 
 def workload_config(S, world, scale):
