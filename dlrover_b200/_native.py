@@ -40,6 +40,7 @@ _SIGNATURES = {
     "fc_ctx_create": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(_vp)]),
     "fc_ctx_destroy": (ctypes.c_int, [_vp]),
     "fc_arena_reserve": (ctypes.c_int, [_vp, _u64]),
+    "fc_set_arena_limit": (ctypes.c_int, [_vp, _u64]),
     "fc_arena_info": (ctypes.c_int, [_vp, ctypes.POINTER(_vp), ctypes.POINTER(_u64)]),
     "fc_host_register": (ctypes.c_int, [_vp, _vp, _u64, ctypes.c_int]),
     "fc_host_unregister": (ctypes.c_int, [_vp, _vp]),
@@ -240,6 +241,9 @@ class Context:
     # -- arena / host segment ------------------------------------------------
     def arena_reserve(self, nbytes: int):
         _check(load_library().fc_arena_reserve(self.handle, int(nbytes)), "fc_arena_reserve")
+
+    def set_arena_limit(self, nbytes: int):
+        _check(load_library().fc_set_arena_limit(self.handle, int(nbytes)), "fc_set_arena_limit")
 
     def arena_info(self) -> Tuple[int, int]:
         p, n = _vp(), _u64()

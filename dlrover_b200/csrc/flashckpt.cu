@@ -551,6 +551,7 @@ struct fc_ctx {
   cudaStream_t copy_stream = nullptr;
   uint8_t* arena = nullptr;
   uint64_t arena_bytes = 0;
+  uint64_t arena_cap = 0;  // 0 = unlimited; else fc_arena_reserve never allocates more
   // tuning
   // tuning: defaults picked from the B200 sweep in profiles/r01_sweep.md
   int variant = FC_VARIANT_TMA;
@@ -654,6 +655,7 @@ struct fc_plan {
   uint64_t payload = 0, arena_end = 0;
   uint32_t chunk = kDefaultChunk;
   std::vector<FcRun> runs;
+  std::vector<FcItem> h_all;  // host copy of `all`, ascending arena offset (windowed mode)
   cudaEvent_t ev_upload = nullptr;  // last table upload
   cudaEvent_t ev_last_use = nullptr;  // last kernel that read the tables
 };
@@ -762,6 +764,7 @@ static int refresh_inflight(fc_ctx* c) {
 extern "C" int fc_arena_reserve(fc_ctx* c, uint64_t bytes) {
   if (!c) return fail(FC_EINVAL, "fc_arena_reserve: null ctx%s%s");
   FC_GUARD(c);
+  if (c->arena_cap && bytes > c->arena_cap) bytes = c->arena_cap;
   if (bytes <= c->arena_bytes) return FC_OK;
   int rc = refresh_inflight(c);
   if (rc) return rc;
@@ -785,6 +788,14 @@ extern "C" int fc_arena_reserve(fc_ctx* c, uint64_t bytes) {
     return fail(FC_ENOMEM, "cudaMalloc(arena): %s", cudaGetErrorString(e));
   }
   c->arena_bytes = bytes;
+  return FC_OK;
+}
+
+extern "C" int fc_set_arena_limit(fc_ctx* c, uint64_t bytes) {
+  if (!c) return fail(FC_EINVAL, "fc_set_arena_limit: null ctx%s%s");
+  if (bytes && bytes < (8ull << 20))
+    return fail(FC_EINVAL, "fc_set_arena_limit: at least 8 MiB%s%s");
+  c->arena_cap = bytes;
   return FC_OK;
 }
 
@@ -1015,6 +1026,8 @@ static int plan_fill(fc_plan* p, uint32_t n, const void* const* dev_ptrs,
     if (tail) split_range(resid, tp + head + body, off + head + body, tail, chunk_bytes);
   }
   if (all.size() > 0xFFFFFFF0ull) return fail(FC_EINVAL, "plan: too many work items%s%s");
+  std::stable_sort(all.begin(), all.end(),
+                   [](const FcItem& a, const FcItem& b) { return a.aoff < b.aoff; });
   int rc = table_set(c, p->all, all, s, sync);
   if (!rc) rc = table_set(c, p->bulk, bulk, s, sync);
   if (!rc) rc = table_set(c, p->resid, resid, s, sync);
@@ -1023,6 +1036,7 @@ static int plan_fill(fc_plan* p, uint32_t n, const void* const* dev_ptrs,
   p->payload = payload;
   p->arena_end = arena_end;
   p->runs.swap(runs);
+  p->h_all.swap(all);
   return FC_OK;
 }
 
@@ -1206,6 +1220,119 @@ extern "C" int fc_unpack_async(fc_plan* p, void* stream, int variant) {
   return launch_copy<1>(p, (cudaStream_t)stream, variant);
 }
 
+// ---- bounded arena ("windowed") mode ---------------------------------------------
+// When the state does not fit a second time in HBM (arena smaller than the
+// plan: fc_set_arena_limit, or the full-size cudaMalloc failed) the checkpoint is
+// streamed through the arena window by window: gather the items of one window
+// (LSU kernel over a slice of the offset-sorted table), DMA the window's bytes,
+// next window.  The tensors must not change until the LAST window has been
+// gathered, so this mode blocks the caller for the whole checkpoint — the
+// reference's behaviour, at PCIe instead of pageable-copy speed.
+struct Window {
+  uint32_t i0, i1;      // item index range in h_all / d_all
+  uint64_t base, end;   // arena byte range covered
+};
+
+static std::vector<Window> make_windows(const fc_plan* p, uint64_t arena_bytes) {
+  std::vector<Window> w;
+  const std::vector<FcItem>& it = p->h_all;
+  uint32_t i = 0, n = (uint32_t)it.size();
+  while (i < n) {
+    Window cur{i, i, it[i].aoff, it[i].aoff};
+    while (cur.i1 < n && it[cur.i1].aoff + it[cur.i1].nbytes - cur.base <= arena_bytes) {
+      cur.end = std::max<uint64_t>(cur.end, it[cur.i1].aoff + it[cur.i1].nbytes);
+      ++cur.i1;
+    }
+    if (cur.i1 == cur.i0) return {};  // one item larger than the arena: cannot happen (>= 8 MiB)
+    w.push_back(cur);
+    i = cur.i1;
+  }
+  return w;
+}
+
+// DMA the parts of the plan's runs that fall into [lo, hi), one piece at a time.
+template <bool TO_HOST>
+static int copy_window(fc_ctx* c, const fc_plan* p, uint8_t* host, uint64_t lo, uint64_t hi,
+                       uint64_t base) {
+  for (const FcRun& r : p->runs) {
+    uint64_t a = std::max(lo, r.off), b = std::min(hi, r.off + r.len);
+    for (uint64_t o = a; o < b; o += c->drain_piece) {
+      const uint64_t len = std::min<uint64_t>(c->drain_piece, b - o);
+      if (TO_HOST)
+        FC_CUDA(cudaMemcpyAsync(host + o, c->arena + (o - base), len, cudaMemcpyDeviceToHost,
+                                c->copy_stream));
+      else
+        FC_CUDA(cudaMemcpyAsync(c->arena + (o - base), host + o, len, cudaMemcpyHostToDevice,
+                                c->copy_stream));
+      c->n_memcpys += 1;
+      FC_CUDA(cudaStreamSynchronize(c->copy_stream));  // paced: one piece in flight
+    }
+  }
+  return FC_OK;
+}
+
+static int save_windowed(fc_plan* p, uint8_t* host, cudaStream_t cs) {
+  fc_ctx* c = p->ctx;
+  std::vector<Window> wins = make_windows(p, c->arena_bytes);
+  if (wins.empty() && !p->h_all.empty())
+    return fail(FC_EINVAL, "arena window too small for a work item%s%s");
+  FC_CUDA(cudaStreamWaitEvent(cs, p->ev_upload, 0));
+  FC_CUDA(cudaEventRecord(c->ev_pack_start, cs));
+  bool first = true;
+  for (const Window& w : wins) {
+    // arena - base: the kernel adds the item's absolute arena offset
+    uint32_t n = w.i1 - w.i0;
+    uint32_t grid = std::min<uint32_t>(n, (uint32_t)(c->sm_count * c->lsu_ctas_per_sm));
+    fc_copy_lsu<0><<<grid, kLsuThreads, 0, cs>>>(p->all.dev + w.i0, n, c->arena - w.base);
+    FC_CUDA(cudaGetLastError());
+    c->n_kernels += 1;
+    FC_CUDA(cudaEventRecord(c->ev_pack_end, cs));
+    FC_CUDA(cudaStreamWaitEvent(c->copy_stream, c->ev_pack_end, 0));
+    if (first) {
+      FC_CUDA(cudaEventRecord(c->ev_drain_start, c->copy_stream));
+      first = false;
+    }
+    int rc = copy_window<true>(c, p, host, w.base, w.end, w.base);
+    if (rc) return rc;
+    // the next gather overwrites the window: it must wait for this drain
+    FC_CUDA(cudaEventRecord(c->ev_drain_end, c->copy_stream));
+    FC_CUDA(cudaStreamWaitEvent(cs, c->ev_drain_end, 0));
+  }
+  if (first) FC_CUDA(cudaEventRecord(c->ev_drain_start, c->copy_stream));
+  FC_CUDA(cudaEventRecord(c->ev_pack_end, cs));
+  FC_CUDA(cudaEventRecord(p->ev_last_use, cs));
+  FC_CUDA(cudaEventRecord(c->ev_drain_end, c->copy_stream));
+  FC_CUDA(cudaEventSynchronize(c->ev_drain_end));
+  FC_CUDA(cudaEventSynchronize(c->ev_pack_end));
+  return FC_OK;
+}
+
+static int restore_windowed(fc_plan* p, const uint8_t* host, cudaStream_t s) {
+  fc_ctx* c = p->ctx;
+  std::vector<Window> wins = make_windows(p, c->arena_bytes);
+  if (wins.empty() && !p->h_all.empty())
+    return fail(FC_EINVAL, "arena window too small for a work item%s%s");
+  FC_CUDA(cudaStreamWaitEvent(s, p->ev_upload, 0));
+  FC_CUDA(cudaEventRecord(c->ev_fill_start, c->copy_stream));
+  for (const Window& w : wins) {
+    int rc = copy_window<false>(c, p, const_cast<uint8_t*>(host), w.base, w.end, w.base);
+    if (rc) return rc;
+    FC_CUDA(cudaEventRecord(c->ev_fill_end, c->copy_stream));
+    FC_CUDA(cudaStreamWaitEvent(s, c->ev_fill_end, 0));
+    uint32_t n = w.i1 - w.i0;
+    uint32_t grid = std::min<uint32_t>(n, (uint32_t)(c->sm_count * c->lsu_ctas_per_sm));
+    fc_copy_lsu<1><<<grid, kLsuThreads, 0, s>>>(p->all.dev + w.i0, n, c->arena - w.base);
+    FC_CUDA(cudaGetLastError());
+    c->n_kernels += 1;
+    FC_CUDA(cudaEventRecord(c->ev_scatter_end, s));
+    FC_CUDA(cudaEventSynchronize(c->ev_scatter_end));  // window is reused by the next fill
+  }
+  FC_CUDA(cudaEventRecord(c->ev_fill_end, c->copy_stream));
+  FC_CUDA(cudaEventRecord(p->ev_last_use, s));
+  FC_CUDA(cudaEventRecord(c->ev_scatter_end, s));
+  return FC_OK;
+}
+
 extern "C" int fc_save_async(fc_plan* p, void* host_base, void* compute_stream, uint64_t* ticket) {
   if (!p || (!host_base && p->payload)) return fail(FC_EINVAL, "fc_save_async: null argument%s%s");
   fc_ctx* c = p->ctx;
@@ -1215,6 +1342,17 @@ extern "C" int fc_save_async(fc_plan* p, void* host_base, void* compute_stream, 
   if (c->save_inflight || c->restore_inflight)
     return fail(FC_EBUSY, "fc_save_async: previous save/restore still draining%s%s");
   cudaStream_t cs = (cudaStream_t)compute_stream;
+  if (p->arena_end > c->arena_bytes) {
+    if (c->arena_bytes < (8ull << 20))
+      return fail(FC_EINVAL, "arena smaller than the plan: call fc_arena_reserve first%s%s");
+    rc = save_windowed(p, static_cast<uint8_t*>(host_base), cs);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(c->mu);
+    c->ticket += 1;
+    c->drained_ticket = c->ticket;  // already complete
+    if (ticket) *ticket = c->ticket;
+    return FC_OK;
+  }
   FC_CUDA(cudaEventRecord(c->ev_pack_start, cs));
   rc = launch_copy<0>(p, cs, FC_VARIANT_AUTO);
   if (rc) return rc;
@@ -1404,8 +1542,14 @@ extern "C" int fc_restore_async(fc_plan* p, const void* host_base, void* stream)
   if (rc) return rc;
   if (c->save_inflight || c->restore_inflight)
     return fail(FC_EBUSY, "fc_restore_async: arena busy%s%s");
-  if (p->arena_end > c->arena_bytes)
-    return fail(FC_EINVAL, "arena smaller than the plan: call fc_arena_reserve first%s%s");
+  if (p->arena_end > c->arena_bytes) {
+    if (c->arena_bytes < (8ull << 20))
+      return fail(FC_EINVAL, "arena smaller than the plan: call fc_arena_reserve first%s%s");
+    rc = restore_windowed(p, static_cast<const uint8_t*>(host_base), (cudaStream_t)stream);
+    if (rc) return rc;
+    c->restore_inflight = true;
+    return FC_OK;
+  }
   cudaStream_t s = (cudaStream_t)stream;
   const uint8_t* hb = static_cast<const uint8_t*>(host_base);
   FC_CUDA(cudaEventRecord(c->ev_fill_start, c->copy_stream));

@@ -228,12 +228,35 @@ class _DeviceStager:
         if plan is not None and plan.key == key:
             return plan
         end = max((o + n for o, n in zip(offs, lens)), default=0)
-        self.ctx.arena_reserve(end)
+        self._reserve_arena(end)
         if plan is None:
             plan = self._plans[role] = self.ctx.plan(ptrs, offs, lens)
         else:
             plan.update(ptrs, offs, lens, stream)
         return plan
+
+    def _reserve_arena(self, end: int):
+        """Full-size arena when HBM allows (the training stream then only waits
+        for the gather kernel); otherwise a bounded arena through which the
+        checkpoint is streamed window by window (blocking, PCIe speed).
+        DLROVER_B200_ARENA_LIMIT_MB forces a cap."""
+        forced = int(os.getenv("DLROVER_B200_ARENA_LIMIT_MB", "0") or 0)
+        if forced:
+            self.ctx.set_arena_limit(max(8, forced) << 20)
+        try:
+            self.ctx.arena_reserve(end)
+            return
+        except native.NativeError as e:
+            if e.code != native.FC_ENOMEM:
+                raise
+        free, _ = torch.cuda.mem_get_info(self.device_index)
+        limit = max(64 << 20, min(end, free // 2))
+        logger.warning(
+            f"No room for a {end / 2**30:.1f} GiB snapshot arena in HBM ({free / 2**30:.1f} GiB "
+            f"free): streaming the checkpoint through a {limit / 2**30:.2f} GiB window; saves "
+            "block until the data is in shared memory.")
+        self.ctx.set_arena_limit(limit)
+        self.ctx.arena_reserve(limit)
 
     def close(self):
         for p in self._plans.values():

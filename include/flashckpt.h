@@ -76,6 +76,13 @@ int fc_ctx_destroy(fc_ctx* ctx);
  * resume after an HBM-speed snapshot instead of after the PCIe copy. */
 int fc_arena_reserve(fc_ctx* ctx, uint64_t bytes);
 int fc_arena_info(fc_ctx* ctx, void** dev_ptr, uint64_t* bytes);
+/* Cap the arena (0 = no cap, minimum 8 MiB).  A plan larger than the arena is
+ * then streamed through it window by window by fc_save_async/fc_restore_async
+ * (gather window -> DMA -> next window).  The tensors must stay unchanged until
+ * the last window is gathered, so in this mode fc_save_async returns only when
+ * the whole checkpoint is in host memory (the reference's blocking behaviour,
+ * at PCIe speed).  Use when the state does not fit in HBM a second time. */
+int fc_set_arena_limit(fc_ctx* ctx, uint64_t bytes);
 
 /* Pin (cudaHostRegister) a host range the CALLER mapped — the POSIX shm
  * segment of multi_process.py:696-734 / ckpt_saver.py:164-195 — so the drain

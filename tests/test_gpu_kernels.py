@@ -220,3 +220,38 @@ def test_plan_update_retargets_without_recreating(cuda_device, variant):
     got = _arena_bytes(ctx, 64 + a[1].numel())
     assert np.array_equal(got[64:], oracle.tensor_bytes(a[1]))
     plan.destroy()
+
+
+def test_bounded_arena_streams_window_by_window(cuda_device):
+    """Plan (45 MB, ragged + misaligned) bigger than the arena (8 MiB cap):
+    fc_save_async/fc_restore_async stream it through the window; bytes equal the
+    oracle image, restore is bit-exact."""
+    ctx = native.Context(0)  # private context: the cap must not leak into other tests
+    ctx.set_arena_limit(8 << 20)
+    g = torch.Generator().manual_seed(5)
+    sizes = [3, 5 << 20, 1, 7 << 20, 123_457, 9 << 20, 6 << 20, 17, 12 << 20, 4 << 20, 999]
+    tensors = [torch.randint(0, 256, (n,), dtype=torch.uint8, generator=g).cuda() for n in sizes]
+    offs, o = [], 0
+    for t in tensors:
+        offs.append(o)
+        o += t.numel()
+    ctx.arena_reserve(o)
+    assert ctx.arena_info()[1] == 8 << 20
+    plan = ctx.plan([t.data_ptr() for t in tensors], offs, sizes)
+    host = torch.zeros(o, dtype=torch.uint8).pin_memory()
+    k0, m0 = ctx.launch_count()
+    ticket = plan.save_async(host.data_ptr(), torch.cuda.current_stream())
+    assert ctx.save_poll(ticket)  # windowed saves complete before returning
+    k1, m1 = ctx.launch_count()
+    assert k1 - k0 >= 6  # ceil(45 MB / 8 MiB) windows, one gather kernel each
+    want = oracle.pack_ranges([oracle.tensor_bytes(t) for t in tensors], offs, o)
+    assert np.array_equal(host.numpy(), want)
+    keep = [t.clone() for t in tensors]
+    for t in tensors:
+        t.zero_()
+    plan.restore_async(host.data_ptr(), torch.cuda.current_stream())
+    ctx.restore_wait()
+    for a, b in zip(tensors, keep):
+        assert torch.equal(a, b)
+    plan.destroy()
+    ctx.destroy()
