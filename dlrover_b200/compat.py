@@ -104,6 +104,66 @@ def install(force: bool = False) -> bool:
     return True
 
 
+# classes whose pickles cross the trainer <-> agent boundary, and the reference
+# module each one is known under on the wire
+_WIRE_CLASSES = {
+    "dlrover.python.common.multi_process": (
+        "dlrover_b200.common.multi_process",
+        ["SocketRequest", "SocketResponse", "LockAcquireResponse", "LockedResponse",
+         "QueueGetResponse", "QueueSizeResponse", "QueueEmptyResponse", "DictMessage"]),
+    "dlrover.python.common.serialize": ("dlrover_b200.common.serialize", ["ClassMeta"]),
+    "dlrover.python.common.storage": (
+        "dlrover_b200.common.storage",
+        ["PosixDiskStorage", "PosixStorageWithDeletion", "KeepStepIntervalStrategy",
+         "KeepLatestStepStrategy"]),
+    "dlrover.python.elastic_agent.torch.ckpt_saver": (
+        "dlrover_b200.ckpt_saver",
+        ["TensorMeta", "CheckpointConfig", "CheckpointEvent", "CheckpointEventType",
+         "DdpCheckpointSaver", "MegatronCheckpointSaver", "DeepSpeedCheckpointSaver",
+         "FsdpDcpSaver", "CommonDirCheckpointSaver", "TempDirCheckpointSaver"]),
+    "dlrover.trainer.torch.flash_checkpoint.fsdp_engine": (
+        "dlrover_b200.flash_checkpoint.fsdp_engine", ["_StorageInfo", "_StoragePrefix"]),
+}
+
+
+def enable_wire_compat() -> None:
+    """Make this package's trainer half interoperable with the REFERENCE's agent
+    half (a job launched with the reference's `dlrover-run`), and vice versa.
+
+    Control messages, the meta tree and the saver/storage descriptors are
+    pickles; pickle records `cls.__module__`.  After this call the listed
+    classes claim the reference's module paths, and those paths resolve (in
+    THIS process) to this package's modules, so what we send is what the
+    reference would have sent, and what the reference sends unpickles into our
+    classes.  Parent packages of an installed reference distribution are left
+    in place — only the aliased modules are overridden.
+    Also triggered by DLROVER_B200_WIRE_COMPAT=1 at `import dlrover_b200`.
+    """
+    for ref_mod, (our_mod, names) in _WIRE_CLASSES.items():
+        ours = importlib.import_module(our_mod)
+        parts = ref_mod.split(".")
+        # parents: keep real ones when importable, else empty stub packages
+        for i in range(1, len(parts)):
+            pkg = ".".join(parts[:i])
+            if pkg in sys.modules:
+                continue
+            try:
+                importlib.import_module(pkg)
+            except Exception:
+                m = types.ModuleType(pkg)
+                m.__path__ = []
+                m.__dlrover_b200_alias__ = True
+                sys.modules[pkg] = m
+                if i > 1:
+                    setattr(sys.modules[".".join(parts[:i - 1])], parts[i - 1], m)
+        sys.modules[ref_mod] = ours
+        setattr(sys.modules[".".join(parts[:-1])], parts[-1], ours)
+        for name in names:
+            cls = getattr(ours, name)
+            cls.__module__ = ref_mod
+    # shm_handler defines TensorMeta/CheckpointConfig; ckpt_saver re-exports them
+
+
 def uninstall():
     for name in [n for n, m in sys.modules.items()
                  if getattr(m, "__dlrover_b200_alias__", False) or
