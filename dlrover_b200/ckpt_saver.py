@@ -72,6 +72,17 @@ class CheckpointEvent:
     global_shard_num: int = 0
 
 
+def _reference_master_client():
+    try:
+        from dlrover.python.elastic_agent.master_client import MasterClient  # type: ignore
+    except Exception:
+        return None
+    try:
+        return MasterClient.singleton_instance()
+    except Exception:
+        return None
+
+
 def _same_path(a: str, b: str) -> bool:
     return os.path.normpath(a) == os.path.normpath(b)
 
@@ -214,6 +225,11 @@ class AsyncCheckpointSaver(metaclass=ABCMeta):
 
     # -- small accessors -------------------------------------------------------------------
     def get_master_client(self):
+        """The job master's client, if there is one: an injected object
+        (set_master_client), else — when this code runs inside the reference's
+        agent (`dlrover-run`) — the reference's MasterClient singleton."""
+        if self._master_client is None:
+            self._master_client = _reference_master_client()
         return self._master_client
 
     def set_master_client(self, client):
@@ -711,17 +727,27 @@ class DeepSpeedCheckpointSaver(_ExtraTrackerSaver):
         return os.path.dirname(spec.origin) if spec and spec.origin else ""
 
     def ucp(self, input_dir: str, output_dir: str, ucp_device_type: str):
-        """Run DeepSpeed's ds_to_universal.py on a saved checkpoint."""
-        import subprocess
+        """Convert a saved checkpoint to DeepSpeed's universal format by running
+        deepspeed/checkpoint/ds_to_universal.py in a child process (started with
+        torchelastic's SubprocessHandler, like the agent's workers)."""
         import sys
 
-        cmd = [os.getenv("PYTHON_EXEC", sys.executable),
-               os.path.join(self.get_deepspeed_install_dir(), "checkpoint", "ds_to_universal.py"),
-               "--input_folder", str(input_dir), "--output_folder", str(output_dir),
-               "--inject_missing_state"]
+        from packaging import version
+        from torch.distributed.elastic.multiprocessing.api import SubprocessHandler
+
+        script = self.get_deepspeed_install_dir() + "/checkpoint/ds_to_universal.py"
+        args = [script, "--input_folder", f"{input_dir}", "--output_folder", f"{output_dir}",
+                "--inject_missing_state"]
         if ucp_device_type != "cpu":
-            cmd += ["--device", ucp_device_type]
-        ret = subprocess.call(cmd)
+            args += ["--device", ucp_device_type]
+        python = os.getenv("PYTHON_EXEC", sys.executable)
+        # SubprocessHandler grew a local_rank_id argument after torch 2.2
+        torch_release = version.parse(version.parse(torch.__version__).base_version)
+        if torch_release <= version.parse("2.2.2"):
+            handler = SubprocessHandler(python, tuple(args), {}, "", "")
+        else:
+            handler = SubprocessHandler(python, tuple(args), {}, "", "", 0)
+        ret = handler.proc.wait()
         if ret != 0:
             logger.error(f"ds_to_universal returned non-zero exit code {ret}")
             return False

@@ -140,11 +140,53 @@ def _stage_items(files: List[Tuple[str, WriteItem]], planner: SavePlanner):
     return results, no_shard, device_ranges, host_ranges, raw_chunks, offset
 
 
-def _write_memory_from_list(shm_handler: SharedMemoryHandler,
-                            files: List[Tuple[str, WriteItem]], planner: SavePlanner,
-                            blocking: bool = True):
+def _write_item(shm, offset, data, write_item, storage_key) -> Tuple[int, WriteResult]:
+    """Write ONE host-resident item at `offset` of a mapped segment and return
+    (next offset, WriteResult) — the reference's per-item helper
+    (fsdp_engine.py:133-155), kept for callers that drive a raw SharedMemory.
+    Device-resident tensors do not go through here: SharedMemoryWriter batches
+    them into one gather kernel."""
+    if write_item.type == WriteItemType.BYTE_IO:
+        assert isinstance(data, io.BytesIO)
+        view = data.getbuffer()
+        length = view.nbytes
+        shm.buf[offset:offset + length] = view
+    else:
+        assert isinstance(data, torch.Tensor)
+        if data.is_cuda:
+            raise ValueError("_write_item handles host tensors only; CUDA items are written "
+                             "by SharedMemoryWriter.write_data in one batch")
+        length = data.numel() * data.element_size()
+        if length:
+            src = data.detach().contiguous()
+            from .. import _native
+
+            _native.host_pack(shm.address, [src.data_ptr()], [offset], [length], 1)
+    result = WriteResult(index=write_item.index, size_in_bytes=length,
+                         storage_data=_StorageInfo(storage_key, offset, length))
+    return offset + length, result
+
+
+def _write_memory_from_list(shm_handler=None, files=None, planner=None, blocking: bool = True,
+                            shm=None):
     """Write all items of `files` into the handler's segment (sized on demand).
-    Returns (write_results, no_shard_data, pending)."""
+    Returns (write_results, no_shard_data, pending).
+
+    Called with a raw mapped segment (`shm=`, the reference's signature,
+    fsdp_engine.py:85-107) it writes host-resident items one by one and
+    returns (write_results, no_shard_data)."""
+    if shm is not None or not hasattr(shm_handler, "write_ranges"):
+        segment = shm if shm is not None else shm_handler
+        results, no_shard, offset = [], {}, 0
+        for storage_key, item in files:
+            data = planner.resolve_data(item)
+            if torch.is_tensor(data):
+                data = data.detach()
+            if item.type != WriteItemType.SHARD:
+                no_shard[item.index.fqn] = data
+            offset, res = _write_item(segment, offset, data, item, storage_key)
+            results.append(res)
+        return results, no_shard
     results, no_shard, dev, host, raw, total = _stage_items(files, planner)
     if total > 0:
         shm_handler.ensure_segment(total)

@@ -140,9 +140,15 @@ class ShardCkptReplicaManager(CkptReplicaManger):
                 h = SharedMemoryHandler(local_rank=rank)
                 h.init_shared_memory()
                 holders[rank] = h
+        return self._gather_owner_checkpoint(holders)
+
+    def _gather_owner_checkpoint(self, shm_handlers):
+        """One exchange round per group member.  `shm_handlers`: what this rank
+        holds for every member — a dict keyed by rank, or a sequence in
+        backup_ranks order."""
         found_bytes, found_meta = None, {}
-        for rank in self.backup_ranks:
-            h = holders[rank]
+        for i, rank in enumerate(self.backup_ranks):
+            h = shm_handlers[rank] if isinstance(shm_handlers, dict) else shm_handlers[i]
             if h.shared_memory:
                 raw, meta = _segment_bytes(h), h.metadata.get()
             else:
@@ -163,11 +169,12 @@ class FullCkptReplicaManager(CkptReplicaManger):
 
     def __init__(self, replica_count=0) -> None:
         super().__init__(replica_count)
-        self.backup_ranks = [node * self.local_world_size for node in range(self.node_num)]
+        self.backup_ranks = self._get_backup_ranks()
         self._make_group()
 
     def _get_backup_ranks(self):
-        return list(self.backup_ranks)
+        """Local rank 0 of every node."""
+        return [node * self.local_world_size for node in range(self.node_num)]
 
     def backup(self, shm_handler: SharedMemoryHandler):
         pass
