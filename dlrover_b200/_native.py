@@ -12,7 +12,7 @@ from __future__ import annotations
 import ctypes
 import os
 import threading
-from typing import Iterable, List, Optional, Sequence, Tuple
+from typing import Optional, Sequence, Tuple
 
 _LIB_NAME = "libflashckpt.so"
 _LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", _LIB_NAME)

@@ -19,7 +19,6 @@ from __future__ import annotations
 import os
 from typing import Dict
 
-import torch
 import torch.distributed as dist
 
 from ..ckpt_saver import DeepSpeedCheckpointSaver

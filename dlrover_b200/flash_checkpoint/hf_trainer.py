@@ -29,7 +29,6 @@ import re
 import shutil
 from typing import Optional
 
-import torch
 import torch.distributed as dist
 
 from ..common.log import default_logger as logger

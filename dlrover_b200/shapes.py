@@ -5,7 +5,7 @@ agnostic, but values are seeded and non-trivial so corruption shows)."""
 from __future__ import annotations
 
 from collections import OrderedDict
-from typing import Dict, Iterator, List, Tuple
+from typing import Dict, List, Tuple
 
 import torch
 
