@@ -10,18 +10,25 @@
 //   2. ONE persistent gather kernel copies all leaves into a contiguous HBM
 //      arena that is a byte image of the segment (pack), HBM-bandwidth bound:
 //      algorithmic traffic 2*S bytes per save;
-//   3. the arena is drained to the (pinned) POSIX shm segment by DMA on a side
-//      stream gated by an event — the training stream only ever waits for (2);
-//   4. restore is the inverse: DMA fill + scatter kernel.
+//   3. the arena is drained to the (pinned, NUMA-local) POSIX shm segment by DMA
+//      on a side stream gated by an event — the training stream only ever waits
+//      for (2).  A pump thread feeds the copy engine ONE 32 MiB piece at a time
+//      so the drain does not starve the application's own D2H copies;
+//   4. restore is the inverse: DMA fill + scatter kernel;
+//   5. if the state does not fit in HBM a second time, (2)+(3) run window by
+//      window through a bounded arena (blocking, PCIe speed).
 //
-// Two kernel families, both templated on direction:
-//   fc_copy_lsu : 256-thread CTAs, 128-bit LDG/STG, 4-way unrolled; handles any
-//                 byte alignment: a <16 B head/tail peel, and when source and
-//                 destination are not congruent mod 16 it loads two aligned
-//                 16-B words and byte-funnels them (both sides stay aligned).
-//   fc_copy_tma : one elected thread per CTA drives a ring of cp.async.bulk
-//                 global->shared (mbarrier complete_tx) and shared->global
-//                 (bulk_group) transfers; used for the 16-B congruent bodies.
+// Three kernels, all templated on direction (0 = gather/pack, 1 = scatter):
+//   fc_copy_tma       one elected thread per CTA drives a ring of cp.async.bulk
+//                     global->shared (mbarrier complete_tx) and shared->global
+//                     (bulk_group) transfers: the 16-B congruent bodies.
+//                     Default 148 CTAs x 2 stages x 96 KiB: 4.76 ms for 32 GB of
+//                     traffic, 1.02x the measured copy peak.
+//   fc_copy_tma_shift ranges whose source and destination are NOT congruent
+//                     mod 16: TMA in, funnel shift shared->shared, TMA out.
+//   fc_copy_lsu       256-thread CTAs, 128-bit LDG/STG, 4-way unrolled: heads,
+//                     tails, tiny ranges, the bounded-arena windows, and
+//                     everything when FC_VARIANT_LSU is selected.
 //
 // No torch types here; see include/flashckpt.h for the ABI contract.
 
