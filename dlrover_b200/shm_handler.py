@@ -25,10 +25,12 @@ fallback for CUDA leaves: a missing library raises.
 
 from __future__ import annotations
 
+import atexit
 import json
 import os
 import threading
 import time
+import weakref
 from collections.abc import Mapping
 from dataclasses import dataclass
 from datetime import datetime
@@ -337,6 +339,12 @@ class SharedMemoryHandler:
         self.last_timings: Optional[Tuple[float, float, float]] = None
         # torch.cuda.Event recorded right after the last gather kernel
         self.last_pack_event = None
+        if not host:
+            # a drain still in flight when the interpreter exits must finish (the
+            # completion thread is a daemon): otherwise the last checkpoint of a
+            # run that ends right after save_checkpoint() would stay half written
+            ref = weakref.ref(self)
+            atexit.register(lambda: ref() is not None and ref()._finish_at_exit())
 
     # -- lifecycle ------------------------------------------------------------------
     def close(self):
@@ -372,6 +380,12 @@ class SharedMemoryHandler:
                           offset=self._buffer_size)
         self._buffer_size += value.numel() * value.element_size()
         return meta
+
+    def _finish_at_exit(self):
+        try:
+            self.wait_pending(timeout=120)
+        except BaseException:
+            pass
 
     # -- pending drain ----------------------------------------------------------------
     def pending_save(self) -> Optional[PendingSave]:
