@@ -66,6 +66,8 @@ _SIGNATURES = {
     "fc_set_launch": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int]),
     "fc_set_shift_launch": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int]),
     "fc_save_async": (ctypes.c_int, [_vp, _vp, _vp, ctypes.POINTER(_u64)]),
+    "fc_save_async_held": (ctypes.c_int, [_vp, _vp, _vp, ctypes.POINTER(_u64)]),
+    "fc_save_release": (ctypes.c_int, [_vp, _u64]),
     "fc_save_pack_done": (ctypes.c_int, [_vp, _u64]),
     "fc_save_poll": (ctypes.c_int, [_vp, _u64]),
     "fc_save_wait": (ctypes.c_int, [_vp, _u64]),
@@ -196,13 +198,12 @@ class Plan:
         _check(load_library().fc_unpack_async(self.handle, _stream_ptr(stream), variant),
                "fc_unpack_async")
 
-    def save_async(self, host_ptr: int, compute_stream=None) -> int:
+    def save_async(self, host_ptr: int, compute_stream=None, hold: bool = False) -> int:
+        """hold=True: gather now, but start the drain only at Context.save_release."""
         ticket = _u64()
-        _check(
-            load_library().fc_save_async(self.handle, host_ptr, _stream_ptr(compute_stream),
-                                         ctypes.byref(ticket)),
-            "fc_save_async",
-        )
+        fn = load_library().fc_save_async_held if hold else load_library().fc_save_async
+        _check(fn(self.handle, host_ptr, _stream_ptr(compute_stream), ctypes.byref(ticket)),
+               "fc_save_async")
         return ticket.value
 
     def restore_async(self, host_ptr: int, stream=None):
@@ -311,6 +312,9 @@ class Context:
                "fc_set_drain")
 
     # -- save / restore tickets ---------------------------------------------------
+    def save_release(self, ticket: int):
+        _check(load_library().fc_save_release(self.handle, ticket), "fc_save_release")
+
     def save_pack_done(self, ticket: int) -> bool:
         return _check(load_library().fc_save_pack_done(self.handle, ticket),
                       "fc_save_pack_done") == FC_OK

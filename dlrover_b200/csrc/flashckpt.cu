@@ -589,6 +589,7 @@ struct fc_ctx {
     std::vector<FcRun> runs;
     uint64_t ticket = 0;
   };
+  uint64_t held_ticket = 0;  // the pump must not start the drain of this ticket yet
   std::deque<DrainJob> jobs;
   bool pump_stop = false;
   uint64_t drained_ticket = 0;  // last ticket whose bytes are all in host memory
@@ -608,8 +609,11 @@ static void pump_main(fc_ctx* c) {
     fc_ctx::DrainJob job;
     {
       std::unique_lock<std::mutex> lk(c->mu);
-      c->cv.wait(lk, [&] { return c->pump_stop || !c->jobs.empty(); });
+      c->cv.wait(lk, [&] {
+        return c->pump_stop || (!c->jobs.empty() && c->jobs.front().ticket != c->held_ticket);
+      });
       if (c->jobs.empty()) return;  // stop requested and nothing queued
+      if (c->jobs.front().ticket == c->held_ticket) c->held_ticket = 0;  // stopping: drain anyway
       job = std::move(c->jobs.front());
       c->jobs.pop_front();
     }
@@ -1340,7 +1344,30 @@ static int restore_windowed(fc_plan* p, const uint8_t* host, cudaStream_t s) {
   return FC_OK;
 }
 
+static int save_async_impl(fc_plan* p, void* host_base, void* compute_stream, uint64_t* ticket,
+                           bool hold);
+
 extern "C" int fc_save_async(fc_plan* p, void* host_base, void* compute_stream, uint64_t* ticket) {
+  return save_async_impl(p, host_base, compute_stream, ticket, false);
+}
+
+extern "C" int fc_save_async_held(fc_plan* p, void* host_base, void* compute_stream,
+                                  uint64_t* ticket) {
+  return save_async_impl(p, host_base, compute_stream, ticket, true);
+}
+
+extern "C" int fc_save_release(fc_ctx* c, uint64_t ticket) {
+  if (!c) return fail(FC_EINVAL, "fc_save_release: null ctx%s%s");
+  {
+    std::lock_guard<std::mutex> lk(c->mu);
+    if (c->held_ticket == ticket) c->held_ticket = 0;
+  }
+  c->cv.notify_all();
+  return FC_OK;
+}
+
+static int save_async_impl(fc_plan* p, void* host_base, void* compute_stream, uint64_t* ticket,
+                           bool hold) {
   if (!p || (!host_base && p->payload)) return fail(FC_EINVAL, "fc_save_async: null argument%s%s");
   fc_ctx* c = p->ctx;
   FC_GUARD(c);
@@ -1374,6 +1401,7 @@ extern "C" int fc_save_async(fc_plan* p, void* host_base, void* compute_stream, 
     job.host = static_cast<uint8_t*>(host_base);
     job.runs = p->runs;
     job.ticket = c->ticket;
+    if (hold) c->held_ticket = c->ticket;
     c->jobs.push_back(std::move(job));
     c->save_inflight = true;
     if (ticket) *ticket = c->ticket;

@@ -273,11 +273,12 @@ class PendingSave:
     """Handle of a save whose drain is still running on the copy stream."""
 
     def __init__(self, ctx: Optional[native.Context], ticket: int, finish: Callable[[], None],
-                 keepalive: list):
+                 keepalive: list, pre_drain: Optional[Callable[[], None]] = None):
         self._ctx = ctx
         self._ticket = ticket
         self._finish = finish
         self._keepalive = keepalive
+        self._pre_drain = pre_drain  # set <=> the drain is held until we release it
         self._done = threading.Event()
         self._error: Optional[BaseException] = None
         self._lock = threading.Lock()
@@ -289,6 +290,11 @@ class PendingSave:
             if self._done.is_set():
                 return
             try:
+                if self._pre_drain is not None:
+                    try:
+                        self._pre_drain()  # e.g. publish writing_shm=True to the agent
+                    finally:
+                        self._ctx.save_release(self._ticket)
                 if self._ctx is not None:
                     self._ctx.save_wait(self._ticket)
                     self.timings = self._ctx.save_timings(self._ticket)
@@ -429,7 +435,8 @@ class SharedMemoryHandler:
 
     def write_ranges(self, device_ranges, host_ranges, raw_chunks=(), *, blocking=True,
                      stream=None, finish: Optional[Callable[[], None]] = None,
-                     keepalive: Optional[list] = None):
+                     keepalive: Optional[list] = None,
+                     pre_drain: Optional[Callable[[], None]] = None):
         """Move bytes into the (already sized) segment.
 
         device_ranges / host_ranges: (tensor, segment offset, nbytes) for CUDA /
@@ -467,12 +474,22 @@ class SharedMemoryHandler:
                 # stream wait for `last_pack_event` before it MUTATES the tensors
                 stream.wait_stream(current)
             plan = stager.plan_for(device_ranges, keepalive, role="save", stream=stream)
-            ticket = plan.save_async(self.shared_memory.address, stream)
+            # bounded-arena saves drain inside save_async: announce first, inline
+            windowed = plan.arena_end > stager.ctx.arena_info()[1]
+            hold = pre_drain is not None and not blocking and not windowed
+            if pre_drain is not None and not hold:
+                pre_drain()
+                pre_drain = None
+            ticket = plan.save_async(self.shared_memory.address, stream, hold=hold)
             ev = torch.cuda.Event()
             ev.record(stream)
             self.last_pack_event = ev
             ctx = stager.ctx
-        pending = PendingSave(ctx, ticket, finish or (lambda: None), keepalive)
+        if ctx is None and pre_drain is not None:
+            pre_drain()
+            pre_drain = None
+        pending = PendingSave(ctx, ticket, finish or (lambda: None), keepalive,
+                              pre_drain=pre_drain if ctx is not None else None)
         self._pending = pending
         if blocking or ctx is None:
             pending._complete()
@@ -501,9 +518,20 @@ class SharedMemoryHandler:
         meta_dict = lay.meta
         conf: CheckpointConfig = meta_dict[DLROVER_CKPT_CONFIG_KEY]
         conf.writing_shm = True
-        report_local_event(EventReportConstants.TYPE_INFO, str(conf.rank),
-                           EventReportConstants.ACTION_MEM_CKPT_START, f"step={conf.step}")
-        self.metadata.set(meta_dict)
+
+        def announce():
+            report_local_event(EventReportConstants.TYPE_INFO, str(conf.rank),
+                               EventReportConstants.ACTION_MEM_CKPT_START, f"step={conf.step}")
+            self.metadata.set(meta_dict)
+
+        # Host-resident leaves are written by this thread right now, so the agent
+        # must already know the segment is changing.  With device leaves only,
+        # nothing touches the segment before the drain: the announcement (a
+        # pickle + two socket round trips) moves to the completion thread and
+        # the drain is held until it is out.
+        defer_announce = (not blocking) and bool(lay.device_leaves) and not lay.host_leaves
+        if not defer_announce:
+            announce()
 
         def finish():
             conf.writing_shm = False
@@ -521,7 +549,8 @@ class SharedMemoryHandler:
         keepalive = [state_dict] if lay.device_leaves else []
         return self.write_ranges(triples(lay.device_leaves), triples(lay.host_leaves),
                                  blocking=blocking, stream=stream, finish=finish,
-                                 keepalive=keepalive)
+                                 keepalive=keepalive,
+                                 pre_drain=announce if defer_announce else None)
 
     def _run_completion(self, pending: PendingSave):
         pending._complete()

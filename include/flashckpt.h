@@ -148,6 +148,12 @@ int fc_set_shift_launch(fc_ctx* ctx, int ctas_per_sm, int in_stages, int tile_by
  * (ckpt_saver.py:198-218). */
 int fc_save_async(fc_plan* plan, void* host_base, void* compute_stream,
                   uint64_t* ticket);
+/* Same, but the drain does not start until fc_save_release(ticket): lets the
+ * caller publish "segment is being written" to its peer from another thread,
+ * off the training thread, before the first byte of the segment changes.
+ * (In the bounded-arena mode the save is complete on return; release is a no-op.) */
+int fc_save_async_held(fc_plan* plan, void* host_base, void* compute_stream, uint64_t* ticket);
+int fc_save_release(fc_ctx* ctx, uint64_t ticket);
 /* FC_OK when the pack kernel of `ticket` has finished (tensors may change). */
 int fc_save_pack_done(fc_ctx* ctx, uint64_t ticket);
 /* FC_OK when all bytes are in host memory, FC_ENOTREADY while pending. */
