@@ -26,6 +26,7 @@ import os
 import pickle
 import re
 import signal
+import sys
 import threading
 import time
 from abc import ABCMeta, abstractmethod
@@ -138,10 +139,8 @@ class AsyncCheckpointSaver(metaclass=ABCMeta):
         self._closed = False
         logger.info(f"AsyncSaver({type(self).__name__}) initialized.")
 
-    def __del__(self):
-        import sys
-
-        if sys.is_finalizing():
+    def __del__(self, _finalizing=sys.is_finalizing):
+        if _finalizing():
             return  # the agent exits: segments are left for the next incarnation
         try:
             self.close()

@@ -344,10 +344,18 @@ class CheckpointEngine(metaclass=ABCMeta):
         try:
             # replica backup issues collectives: keep those on the calling thread
             sync = not self._async_drain or self._replica_manager.has_replica()
+            def failed():
+                # the segment is torn (writing_shm stays set): give the lock back so
+                # later saves are attempted instead of being skipped forever
+                if acquired:
+                    self._shm_lock.release()
+
             self._shm_handler.save_state_dict(state_dict, blocking=sync, on_complete=completed,
-                                              stream=self.snapshot_stream)
+                                              on_error=failed, stream=self.snapshot_stream)
         except BaseException:
-            if acquired and self._shm_handler.pending_save() is None:
+            # raised before a completion thread took over (the blocking path runs
+            # `failed` itself)
+            if acquired and self._shm_handler.pending_save() is None and self._shm_lock.locked():
                 self._shm_lock.release()
             raise
         self._cached_step = conf.step

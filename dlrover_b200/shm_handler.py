@@ -273,7 +273,9 @@ class PendingSave:
     """Handle of a save whose drain is still running on the copy stream."""
 
     def __init__(self, ctx: Optional[native.Context], ticket: int, finish: Callable[[], None],
-                 keepalive: list, pre_drain: Optional[Callable[[], None]] = None):
+                 keepalive: list, pre_drain: Optional[Callable[[], None]] = None,
+                 on_error: Optional[Callable[[], None]] = None):
+        self._on_error = on_error
         self._ctx = ctx
         self._ticket = ticket
         self._finish = finish
@@ -302,6 +304,11 @@ class PendingSave:
             except BaseException as e:  # surfaced by wait()
                 self._error = e
                 logger.error(f"flash checkpoint drain failed: {e}", exc_info=True)
+                if self._on_error is not None:
+                    try:
+                        self._on_error()  # e.g. give the shard lock back
+                    except BaseException:
+                        logger.error("error handler of the failed drain raised", exc_info=True)
             finally:
                 self._keepalive.clear()
                 self._done.set()
@@ -402,7 +409,14 @@ class SharedMemoryHandler:
         p = self._pending
         if p is None:
             return True
-        return p.wait(timeout)
+        try:
+            ok = p.wait(timeout)
+        except BaseException:
+            self._pending = None  # a failed drain is reported once
+            raise
+        if ok:
+            self._pending = None
+        return ok
 
     # -- save ---------------------------------------------------------------------------
     def _stager_for(self, tensors) -> _DeviceStager:
@@ -436,7 +450,8 @@ class SharedMemoryHandler:
     def write_ranges(self, device_ranges, host_ranges, raw_chunks=(), *, blocking=True,
                      stream=None, finish: Optional[Callable[[], None]] = None,
                      keepalive: Optional[list] = None,
-                     pre_drain: Optional[Callable[[], None]] = None):
+                     pre_drain: Optional[Callable[[], None]] = None,
+                     on_error: Optional[Callable[[], None]] = None):
         """Move bytes into the (already sized) segment.
 
         device_ranges / host_ranges: (tensor, segment offset, nbytes) for CUDA /
@@ -489,11 +504,13 @@ class SharedMemoryHandler:
             pre_drain()
             pre_drain = None
         pending = PendingSave(ctx, ticket, finish or (lambda: None), keepalive,
-                              pre_drain=pre_drain if ctx is not None else None)
+                              pre_drain=pre_drain if ctx is not None else None,
+                              on_error=on_error)
         self._pending = pending
         if blocking or ctx is None:
             pending._complete()
             self.last_timings = pending.timings
+            self._pending = None
             pending.wait()  # re-raise a drain error
             return None
         threading.Thread(target=self._run_completion, args=(pending,), name="fc-drain",
@@ -501,7 +518,8 @@ class SharedMemoryHandler:
         return pending
 
     def save_state_dict(self, state_dict, blocking: bool = True, stream=None,
-                        on_complete: Optional[Callable[[], None]] = None):
+                        on_complete: Optional[Callable[[], None]] = None,
+                        on_error: Optional[Callable[[], None]] = None):
         """Serialise `state_dict` into the segment.
 
         blocking=True (the reference's semantics): returns None after every
@@ -550,7 +568,8 @@ class SharedMemoryHandler:
         return self.write_ranges(triples(lay.device_leaves), triples(lay.host_leaves),
                                  blocking=blocking, stream=stream, finish=finish,
                                  keepalive=keepalive,
-                                 pre_drain=announce if defer_announce else None)
+                                 pre_drain=announce if defer_announce else None,
+                                 on_error=on_error)
 
     def _run_completion(self, pending: PendingSave):
         pending._complete()

@@ -263,3 +263,27 @@ def test_snapshot_on_a_side_stream(cuda_device, agent, tmp_path):
     saved = engine.load()["w"]
     assert float(saved.min()) == 3.0 and float(saved.max()) == 3.0
     engine.close()
+
+
+def test_failed_drain_gives_the_lock_back(agent, tmp_path, monkeypatch):
+    """If the completion of a save fails, the shard lock must not stay ours
+    (later saves would be skipped forever) and the error surfaces."""
+    engine = FullCheckpointEngine(str(tmp_path), PosixDiskStorage(), async_drain=False)
+    _, sd = _sd()
+    calls = {"n": 0}
+    real_set = engine._shm_handler.metadata.set
+
+    def flaky_set(meta):
+        calls["n"] += 1
+        if calls["n"] == 2:  # the final writing_shm=False publication
+            raise RuntimeError("agent went away")
+        return real_set(meta)
+
+    monkeypatch.setattr(engine._shm_handler.metadata, "set", flaky_set)
+    with pytest.raises(RuntimeError):
+        engine.save_to_memory(1, {MODEL: sd}, {MODEL: str(tmp_path / "x.pt")})
+    saver = AsyncCheckpointSaver.get_ckpt_saver()
+    assert not saver._shm_locks[0].locked()
+    monkeypatch.setattr(engine._shm_handler.metadata, "set", real_set)
+    assert engine.save_to_memory(2, {MODEL: sd}, {MODEL: str(tmp_path / "x.pt")}) is True
+    engine.close()
