@@ -570,9 +570,34 @@ def measure_cpu_baseline(sd, S):
         saver.close()
     return {"value": S / dt / 1e9, "unit": UNIT, "cores": 1, "host_cores": os.cpu_count(),
             "kind": "port", "ms_per_step": dt * 1e3,
+            "torch_save": measure_torch_save(sd),
             "sample": "2 full saves of the same state_dict through oracle/ref_port.py: "
                       "per-tensor blocking copy_ device->pageable /dev/shm "
                       "(restates ckpt_saver.py:198-231); single host thread, as the reference"}
+
+
+def measure_torch_save(sd, budget_bytes=2 << 30):
+    """B0 of SURVEY §8(d): naive blocking torch.save of device tensors to /dev/shm, on a
+    bounded sample (leading tensors of the state_dict up to ~2 GiB)."""
+    import torch
+
+    sample, size = {}, 0
+    for k, v in sd.items():
+        if size + v.numel() * v.element_size() > budget_bytes and sample:
+            continue
+        sample[k] = v
+        size += v.numel() * v.element_size()
+    path = f"/dev/shm/fc_bench_torch_save_{os.getpid()}.pt"
+    try:
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        torch.save(sample, path)
+        dt = time.perf_counter() - t0
+    finally:
+        if os.path.exists(path):
+            os.remove(path)
+    return {"value": size / dt / 1e9, "unit": UNIT, "bytes": size, "ms": dt * 1e3,
+            "sample": f"torch.save of {len(sample)} tensors ({size / 1e9:.2f} GB) to /dev/shm"}
 
 
 def main():

@@ -186,8 +186,7 @@ class Plan:
         a_len = (_u64 * max(n, 1))(*[int(b) for b in nbytes])
         _check(load_library().fc_plan_update(self.handle, n, a_ptr, a_off, a_len,
                                              _stream_ptr(stream)), "fc_plan_update")
-        self.key = (tuple(int(p) for p in ptrs), tuple(int(o) for o in offsets),
-                    tuple(int(b) for b in nbytes))
+        self.key = ([int(p) for p in ptrs], [int(o) for o in offsets], [int(b) for b in nbytes])
         self._refresh_info()
 
     def pack(self, stream=None, variant: int = VARIANT_AUTO):
@@ -281,8 +280,7 @@ class Context:
                                           ctypes.byref(h)),
             "fc_plan_create",
         )
-        key = (tuple(int(p) for p in ptrs), tuple(int(o) for o in offsets),
-               tuple(int(b) for b in nbytes))
+        key = ([int(p) for p in ptrs], [int(o) for o in offsets], [int(b) for b in nbytes])
         return Plan(self, h.value, key)
 
     def launch_count(self) -> Tuple[int, int]:

@@ -99,36 +99,60 @@ def _traverse_state_dict(value, visitor: Callable):
 class _Layout:
     """Result of one planning walk over a state_dict."""
 
-    __slots__ = ("meta", "total", "device_leaves", "host_leaves", "signature")
+    __slots__ = ("meta", "total", "device_leaves", "host_leaves", "leaf_metas", "reused")
 
     def __init__(self):
         self.meta: Any = None
         self.total = 0
         self.device_leaves: List[Tuple[torch.Tensor, TensorMeta]] = []
         self.host_leaves: List[Tuple[torch.Tensor, TensorMeta]] = []
-        self.signature: Tuple = ()
+        self.leaf_metas: List[TensorMeta] = []  # every tensor leaf, traversal order
+        self.reused = 0  # leaves whose TensorMeta was taken over from `prev`
 
 
-def plan_layout(state_dict) -> _Layout:
-    """Assign every tensor leaf its byte offset (reference layout) and sort the
-    leaves into device-resident and host-resident."""
+def plan_layout(state_dict, prev: Optional["_Layout"] = None) -> _Layout:
+    """Assign every tensor leaf its byte offset (reference layout,
+    ckpt_saver.py:286-301) and sort the leaves into device-resident and
+    host-resident.  This runs on the training thread at every save, so the walk
+    is kept lean: with `prev` (the layout of the previous save) a leaf that
+    still has the same shape/dtype at the same offset takes over its TensorMeta
+    instead of building a new one."""
     lay = _Layout()
-    sig = []
+    metas, dev, host = lay.leaf_metas, lay.device_leaves, lay.host_leaves
+    prev_metas = prev.leaf_metas if prev is not None else ()
+    nprev = len(prev_metas)
+    Tensor = torch.Tensor
+    total = 0
+    reused = 0
 
-    def visit(v):
-        if not torch.is_tensor(v):
-            return v
-        numel, esize = v.numel(), v.element_size()
-        m = TensorMeta(shape=tuple(v.shape), dtype=v.dtype, element_size=esize, numel=numel,
-                       offset=lay.total)
-        lay.total += numel * esize
-        sig.append((m.shape, v.dtype, v.device.type))
-        if numel:
-            (lay.device_leaves if v.is_cuda else lay.host_leaves).append((v, m))
-        return m
+    def walk(value):
+        nonlocal total, reused
+        if isinstance(value, Tensor):
+            i = len(metas)
+            m = prev_metas[i] if i < nprev else None
+            if m is not None and m.offset == total and m.dtype is value.dtype \
+                    and m.shape == value.shape:
+                reused += 1
+            else:
+                m = TensorMeta(shape=tuple(value.shape), dtype=value.dtype,
+                               element_size=value.element_size(), numel=value.numel(),
+                               offset=total)
+            metas.append(m)
+            nbytes = m.numel * m.element_size
+            if nbytes:
+                total += nbytes
+                (dev if value.is_cuda else host).append((value, m))
+            return m
+        kind = type(value)
+        if kind is dict or (kind is not list and isinstance(value, Mapping)):
+            return {k: walk(v) for k, v in value.items()}
+        if kind is list or isinstance(value, list):
+            return [walk(v) for v in value]
+        return value  # non-tensor leaf (tuples included): carried in the meta tree
 
-    lay.meta = _traverse_state_dict(state_dict, visit)
-    lay.signature = tuple(sig)
+    lay.meta = walk(state_dict)
+    lay.total = total
+    lay.reused = reused
     return lay
 
 
@@ -217,17 +241,20 @@ class _DeviceStager:
         One plan object per role ("save" / "restore"); when the tensors moved
         (FSDP hands out fresh ones on every state_dict()) the plan is
         re-targeted in place with a stream-ordered table upload."""
-        ptrs, offs, lens = [], [], []
-        for t, off, nbytes in ranges:
-            if not t.is_contiguous():
-                # rare (state_dict tensors are contiguous); device-side repack,
-                # kept alive until the pack kernel has consumed it
-                t = t.detach().contiguous()
-                keepalive.append(t)
-            ptrs.append(t.data_ptr())
-            offs.append(off)
-            lens.append(nbytes)
-        key = (tuple(ptrs), tuple(offs), tuple(lens))
+        if not all(t.is_contiguous() for t, _, _ in ranges):
+            # rare (state_dict tensors are contiguous); device-side repack,
+            # kept alive until the pack kernel has consumed it
+            packed = []
+            for t, off, nbytes in ranges:
+                if not t.is_contiguous():
+                    t = t.detach().contiguous()
+                    keepalive.append(t)
+                packed.append((t, off, nbytes))
+            ranges = packed
+        ptrs = [t.data_ptr() for t, _, _ in ranges]
+        offs = [r[1] for r in ranges]
+        lens = [r[2] for r in ranges]
+        key = (ptrs, offs, lens)
         plan = self._plans.get(role)
         if plan is not None and plan.key == key:
             return plan
@@ -345,7 +372,7 @@ class SharedMemoryHandler:
         self.metadata = SharedDict(name=CheckpointSharedObjPrefix.META_NAME + str(local_rank),
                                    create=host)
         self._need_creation = True
-        self._signature: Optional[Tuple] = None
+        self._layout: Optional[_Layout] = None  # of the previous save (TensorMeta reuse)
         self._stager: Optional[_DeviceStager] = None
         self._pending: Optional[PendingSave] = None
         self._master_client = None
@@ -529,10 +556,9 @@ class SharedMemoryHandler:
         finishes the protocol and then calls `on_complete`.
         """
         self.wait_pending()
-        lay = plan_layout(state_dict)
+        lay = self._layout = plan_layout(state_dict, self._layout)
         if lay.total > 0:
             self.ensure_segment(lay.total)
-        self._signature = lay.signature
         meta_dict = lay.meta
         conf: CheckpointConfig = meta_dict[DLROVER_CKPT_CONFIG_KEY]
         conf.writing_shm = True
