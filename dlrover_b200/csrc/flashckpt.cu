@@ -878,6 +878,17 @@ extern "C" int fc_host_register(fc_ctx* c, void* host, uint64_t bytes, int prefa
   if (!c || !host || bytes == 0) return fail(FC_EINVAL, "fc_host_register: bad argument%s%s");
   FC_GUARD(c);
   if (!getenv("FC_NO_NUMA")) prefer_numa_node(host, bytes, gpu_numa_node(c->device));
+#ifdef MADV_HUGEPAGE
+  // 2 MiB pages where the host allows them for this mapping (tmpfs: only with
+  // transparent_hugepage/shmem_enabled = advise|always): fewer IOMMU / page-table
+  // entries under the DMA.  Advice only; a refusal changes nothing.
+  if (!getenv("FC_NO_HUGEPAGE")) {
+    const uintptr_t pg = (uintptr_t)sysconf(_SC_PAGESIZE);
+    uintptr_t lo = ((uintptr_t)host + pg - 1) & ~(pg - 1);
+    uintptr_t hi = ((uintptr_t)host + bytes) & ~(pg - 1);
+    if (hi > lo) (void)madvise((void*)lo, hi - lo, MADV_HUGEPAGE);
+  }
+#endif
   if (prefault_threads > 0) {
     const long pg = sysconf(_SC_PAGESIZE);
     int nt = std::min(prefault_threads, 64);
