@@ -210,11 +210,15 @@ def run_reference(args):
         saver.close()
     gbs = S * args.steps / dt / 1e9
     line = {
-        "impl": "reference", "metric": METRIC, "value": gbs, "unit": UNIT, "n_gpus": 1,
+        "impl": "reference", "metric": METRIC, "value": gbs, "unit": UNIT, "n_gpus": world,
+        "ranks_run": 1,
+        "note": "CPU-side reference path timed on rank 0 only (one shard, one host thread, as the "
+                "reference runs it per rank); with N ranks the reference saves N such shards "
+                "independently, so its N-rank aggregate is at most N x this value",
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
         "data": "synthetic",
-        "config": workload_config(S, 1, args.scale),
+        "config": workload_config(S, world, args.scale),
         "stall_ms": {"blocking": dt / args.steps * 1e3,
                      "note": "the reference blocks the training thread for the whole copy"},
         "restore": {"reference_ms": restore_s * 1e3, "reference_GBps": S / restore_s / 1e9,
