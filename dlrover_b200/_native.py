@@ -68,6 +68,9 @@ _SIGNATURES = {
     "fc_save_async": (ctypes.c_int, [_vp, _vp, _vp, ctypes.POINTER(_u64)]),
     "fc_save_async_held": (ctypes.c_int, [_vp, _vp, _vp, ctypes.POINTER(_u64)]),
     "fc_save_release": (ctypes.c_int, [_vp, _u64]),
+    "fc_save_direct_async": (ctypes.c_int, [_vp, _vp, _vp, ctypes.c_int, ctypes.POINTER(_u64)]),
+    "fc_restore_direct_async": (ctypes.c_int, [_vp, _vp, _vp]),
+    "fc_plan_spans": (ctypes.c_int, [_vp, ctypes.POINTER(_u32)]),
     "fc_save_pack_done": (ctypes.c_int, [_vp, _u64]),
     "fc_save_poll": (ctypes.c_int, [_vp, _u64]),
     "fc_save_wait": (ctypes.c_int, [_vp, _u64]),
@@ -170,6 +173,9 @@ class Plan:
         self.n_items = items.value
         self.n_runs = runs.value
         self.arena_end = end.value
+        spans = _u32()
+        _check(lib.fc_plan_spans(self._h, ctypes.byref(spans)), "fc_plan_spans")
+        self.n_spans = spans.value
 
     @property
     def handle(self) -> int:
@@ -205,9 +211,25 @@ class Plan:
                "fc_save_async")
         return ticket.value
 
-    def restore_async(self, host_ptr: int, stream=None):
-        _check(load_library().fc_restore_async(self.handle, host_ptr, _stream_ptr(stream)),
-               "fc_restore_async")
+    def save_direct_async(self, host_ptr: int, compute_stream=None, hold: bool = False) -> int:
+        """In-place save: no snapshot, the drain reads the tensors themselves, which
+        must stay unchanged until the ticket is drained."""
+        ticket = _u64()
+        _check(load_library().fc_save_direct_async(self.handle, host_ptr,
+                                                   _stream_ptr(compute_stream), int(hold),
+                                                   ctypes.byref(ticket)),
+               "fc_save_direct_async")
+        return ticket.value
+
+    def restore_async(self, host_ptr: int, stream=None, direct: bool = False):
+        """direct=True: DMA straight into the target tensors (no arena, no kernel)."""
+        lib = load_library()
+        if direct:
+            _check(lib.fc_restore_direct_async(self.handle, host_ptr, _stream_ptr(stream)),
+                   "fc_restore_direct_async")
+        else:
+            _check(lib.fc_restore_async(self.handle, host_ptr, _stream_ptr(stream)),
+                   "fc_restore_async")
 
     def destroy(self):
         if self._h:

@@ -101,6 +101,12 @@ struct FcRun {  // merged contiguous arena range (drain/fill DMA granularity)
   uint64_t len;
 };
 
+struct FcSpan {  // one source range, merged where tensor AND arena addresses continue
+  uint64_t tptr;
+  uint64_t off;
+  uint64_t len;
+};
+
 constexpr int kLsuThreads = 256;
 constexpr int kLsuUnroll = 4;
 constexpr uint32_t kDefaultChunk = 256u << 10;      // work-item size
@@ -587,8 +593,11 @@ struct fc_ctx {
   struct DrainJob {
     uint8_t* host = nullptr;
     std::vector<FcRun> runs;
+    std::vector<FcSpan> spans;  // in-place save: DMA straight from the tensors
+    bool direct = false;
     uint64_t ticket = 0;
   };
+  uint64_t direct_ticket = 0;  // last ticket saved in place (no snapshot: sources stay frozen)
   uint64_t held_ticket = 0;  // the pump must not start the drain of this ticket yet
   std::deque<DrainJob> jobs;
   bool pump_stop = false;
@@ -621,6 +630,27 @@ static void pump_main(fc_ctx* c) {
     if (e == cudaSuccess) e = cudaEventRecord(c->ev_drain_start, c->copy_stream);
     const int depth = std::max(1, std::min(c->drain_depth, kDrainRing));
     uint64_t k = 0, copies = 0;
+    if (job.direct) {
+      // one batch (<= drain_piece bytes, <= 64 copies) in flight, then wait: same
+      // pacing rule as below, small tensors share a batch
+      uint64_t batch_bytes = 0;
+      int batch_n = 0;
+      for (const FcSpan& sp : job.spans) {
+        for (uint64_t o = 0; o < sp.len && e == cudaSuccess; o += c->drain_piece) {
+          const uint64_t len = std::min<uint64_t>(c->drain_piece, sp.len - o);
+          e = cudaMemcpyAsync(job.host + sp.off + o, (const uint8_t*)(uintptr_t)sp.tptr + o, len,
+                              cudaMemcpyDeviceToHost, c->copy_stream);
+          ++copies;
+          batch_bytes += len;
+          if (e == cudaSuccess && (batch_bytes >= c->drain_piece || ++batch_n >= 64)) {
+            e = cudaEventRecord(c->ring[0], c->copy_stream);
+            if (e == cudaSuccess) e = cudaEventSynchronize(c->ring[0]);
+            batch_bytes = 0;
+            batch_n = 0;
+          }
+        }
+      }
+    }
     for (const FcRun& r : job.runs) {
       for (uint64_t o = 0; o < r.len && e == cudaSuccess; o += c->drain_piece) {
         const uint64_t len = std::min<uint64_t>(c->drain_piece, r.len - o);
@@ -667,6 +697,7 @@ struct fc_plan {
   uint32_t chunk = kDefaultChunk;
   std::vector<FcRun> runs;
   std::vector<FcItem> h_all;  // host copy of `all`, ascending arena offset (windowed mode)
+  std::vector<FcSpan> spans;  // source ranges by arena offset (in-place save / restore)
   cudaEvent_t ev_upload = nullptr;  // last table upload
   cudaEvent_t ev_last_use = nullptr;  // last kernel that read the tables
 };
@@ -1000,13 +1031,16 @@ static int plan_fill(fc_plan* p, uint32_t n, const void* const* dev_ptrs,
   const uint32_t chunk_bytes = p->chunk;
   uint64_t payload = 0, arena_end = 0;
   std::vector<FcRun> ranges, runs;
+  std::vector<FcSpan> spans;
   ranges.reserve(n);
+  spans.reserve(n);
   for (uint32_t i = 0; i < n; ++i) {
     if (nbytes[i] == 0) continue;
     if (!dev_ptrs[i])
       return fail(FC_EINVAL, "plan: null device pointer for a non-empty tensor%s%s");
     if (arena_off[i] + nbytes[i] < arena_off[i]) return fail(FC_EINVAL, "plan: offset overflow%s%s");
     ranges.push_back({arena_off[i], nbytes[i]});
+    spans.push_back({(uint64_t)(uintptr_t)dev_ptrs[i], arena_off[i], nbytes[i]});
     payload += nbytes[i];
     arena_end = std::max(arena_end, arena_off[i] + nbytes[i]);
   }
@@ -1059,6 +1093,19 @@ static int plan_fill(fc_plan* p, uint32_t n, const void* const* dev_ptrs,
   p->arena_end = arena_end;
   p->runs.swap(runs);
   p->h_all.swap(all);
+  std::sort(spans.begin(), spans.end(),
+            [](const FcSpan& a, const FcSpan& b) { return a.off < b.off; });
+  p->spans.clear();
+  for (const FcSpan& sp : spans) {
+    if (!p->spans.empty()) {
+      FcSpan& last = p->spans.back();
+      if (sp.off == last.off + last.len && sp.tptr == last.tptr + last.len) {
+        last.len += sp.len;
+        continue;
+      }
+    }
+    p->spans.push_back(sp);
+  }
   return FC_OK;
 }
 
@@ -1126,6 +1173,12 @@ extern "C" int fc_plan_destroy(fc_plan* p) {
   if (p->ev_upload) cudaEventDestroy(p->ev_upload);
   if (p->ev_last_use) cudaEventDestroy(p->ev_last_use);
   delete p;
+  return FC_OK;
+}
+
+extern "C" int fc_plan_spans(const fc_plan* p, uint32_t* n_spans) {
+  if (!p || !n_spans) return fail(FC_EINVAL, "fc_plan_spans: null argument%s%s");
+  *n_spans = (uint32_t)p->spans.size();
   return FC_OK;
 }
 
@@ -1421,15 +1474,82 @@ static int save_async_impl(fc_plan* p, void* host_base, void* compute_stream, ui
   return FC_OK;
 }
 
+extern "C" int fc_save_direct_async(fc_plan* p, void* host_base, void* compute_stream, int hold,
+                                    uint64_t* ticket) {
+  if (!p || (!host_base && p->payload))
+    return fail(FC_EINVAL, "fc_save_direct_async: null argument%s%s");
+  fc_ctx* c = p->ctx;
+  FC_GUARD(c);
+  int rc = refresh_inflight(c);
+  if (rc) return rc;
+  if (c->save_inflight || c->restore_inflight)
+    return fail(FC_EBUSY, "fc_save_direct_async: previous save/restore still draining%s%s");
+  cudaStream_t cs = (cudaStream_t)compute_stream;
+  // no kernel: the pair of events orders the drain after everything already
+  // queued on the training stream (the optimizer step that produced the values)
+  FC_CUDA(cudaEventRecord(c->ev_pack_start, cs));
+  FC_CUDA(cudaEventRecord(c->ev_pack_end, cs));
+  {
+    std::lock_guard<std::mutex> lk(c->mu);
+    if (c->drain_rc != FC_OK) return fail(c->drain_rc, "%s", c->drain_err.c_str());
+    if (!c->pump.joinable()) c->pump = std::thread(pump_main, c);
+    c->ticket += 1;
+    fc_ctx::DrainJob job;
+    job.host = static_cast<uint8_t*>(host_base);
+    job.spans = p->spans;
+    job.direct = true;
+    job.ticket = c->ticket;
+    if (hold) c->held_ticket = c->ticket;
+    c->direct_ticket = c->ticket;
+    c->jobs.push_back(std::move(job));
+    c->save_inflight = true;
+    if (ticket) *ticket = c->ticket;
+  }
+  c->cv.notify_all();
+  return FC_OK;
+}
+
+extern "C" int fc_restore_direct_async(fc_plan* p, const void* host_base, void* stream) {
+  if (!p || (!host_base && p->payload))
+    return fail(FC_EINVAL, "fc_restore_direct_async: null argument%s%s");
+  fc_ctx* c = p->ctx;
+  FC_GUARD(c);
+  int rc = refresh_inflight(c);
+  if (rc) return rc;
+  if (c->save_inflight || c->restore_inflight)
+    return fail(FC_EBUSY, "fc_restore_direct_async: context busy%s%s");
+  cudaStream_t s = (cudaStream_t)stream;
+  const uint8_t* hb = static_cast<const uint8_t*>(host_base);
+  // the targets may still be read by work queued on `stream`
+  FC_CUDA(cudaEventRecord(c->ev_scatter_end, s));
+  FC_CUDA(cudaStreamWaitEvent(c->copy_stream, c->ev_scatter_end, 0));
+  FC_CUDA(cudaEventRecord(c->ev_fill_start, c->copy_stream));
+  for (const FcSpan& sp : p->spans)
+    for (uint64_t o = 0; o < sp.len; o += kDmaPiece) {
+      uint64_t len = std::min<uint64_t>(kDmaPiece, sp.len - o);
+      FC_CUDA(cudaMemcpyAsync((uint8_t*)(uintptr_t)sp.tptr + o, hb + sp.off + o, len,
+                              cudaMemcpyHostToDevice, c->copy_stream));
+      c->n_memcpys += 1;
+    }
+  FC_CUDA(cudaEventRecord(c->ev_fill_end, c->copy_stream));
+  FC_CUDA(cudaStreamWaitEvent(s, c->ev_fill_end, 0));
+  FC_CUDA(cudaEventRecord(c->ev_scatter_end, s));
+  c->restore_inflight = true;
+  return FC_OK;
+}
+
 static int check_ticket(fc_ctx* c, uint64_t ticket, const char* who) {
   if (!c) return fail(FC_EINVAL, "%s: null ctx", who);
   if (ticket == 0 || ticket != c->ticket) return fail(FC_EINVAL, "%s: unknown ticket", who);
   return FC_OK;
 }
 
+static int drain_status(fc_ctx* c, uint64_t ticket, bool wait);
+
 extern "C" int fc_save_pack_done(fc_ctx* c, uint64_t ticket) {
   int rc = check_ticket(c, ticket, "fc_save_pack_done");
   if (rc) return rc;
+  if (ticket == c->direct_ticket) return drain_status(c, ticket, false);  // no snapshot was taken
   FC_GUARD(c);
   cudaError_t e = cudaEventQuery(c->ev_pack_end);
   if (e == cudaSuccess) return FC_OK;

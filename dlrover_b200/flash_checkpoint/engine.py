@@ -304,8 +304,34 @@ class CheckpointEngine(metaclass=ABCMeta):
     snapshot_stream = None
 
     def pack_done_event(self):
-        """torch.cuda.Event recorded after the gather kernel of the last save."""
+        """torch.cuda.Event recorded after the gather kernel of the last save
+        (None after an in-place save: use wait_snapshot())."""
         return self._shm_handler.last_pack_event
+
+    # In-place saves (opt-in; also DLROVER_B200_IN_PLACE=1): no HBM snapshot, the
+    # drain DMAs straight from the live tensors, so a state that does not fit in HBM
+    # twice (8B weights + fp32 Adam moments = 112 GB) is still saved asynchronously.
+    # Parameters and optimizer state are only written by optimizer.step(): guard it
+    # with engine.guard_optimizer(optimizer) (or call engine.wait_snapshot() yourself
+    # before the first write).  Buffers that the forward pass mutates (BatchNorm
+    # statistics) are not covered — keep the default snapshot mode for such models.
+    @property
+    def in_place(self) -> bool:
+        return self._shm_handler.in_place
+
+    @in_place.setter
+    def in_place(self, value: bool):
+        self._shm_handler.in_place = bool(value)
+
+    def wait_snapshot(self):
+        """Call before the first write to tensors handed to the last save."""
+        self._shm_handler.wait_snapshot()
+
+    def guard_optimizer(self, optimizer):
+        """Make `optimizer.step()` wait until the last save no longer reads the
+        parameters / optimizer state (torch.optim step pre-hook).  Returns the
+        hook handle."""
+        return optimizer.register_step_pre_hook(lambda *_a, **_k: self.wait_snapshot())
 
     def save_state_dict_to_memory(self, state_dict, conf: CheckpointConfig, blocking=False):
         """Returns True when the state dict was (or is being) written to shared

@@ -213,6 +213,7 @@ class _DeviceStager:
         self._registered_addr = 0
         self._plans: Dict[str, native.Plan] = {}  # role -> plan
         self.register_seconds = 0.0
+        self._warned_no_arena = False
 
     def attach(self, shm: SharedMemory):
         addr = shm.address
@@ -258,36 +259,45 @@ class _DeviceStager:
         plan = self._plans.get(role)
         if plan is not None and plan.key == key:
             return plan
-        end = max((o + n for o, n in zip(offs, lens)), default=0)
-        self._reserve_arena(end)
         if plan is None:
             plan = self._plans[role] = self.ctx.plan(ptrs, offs, lens)
         else:
             plan.update(ptrs, offs, lens, stream)
         return plan
 
-    def _reserve_arena(self, end: int):
-        """Full-size arena when HBM allows (the training stream then only waits
-        for the gather kernel); otherwise a bounded arena through which the
-        checkpoint is streamed window by window (blocking, PCIe speed).
-        DLROVER_B200_ARENA_LIMIT_MB forces a cap."""
+    ARENA_FULL, ARENA_WINDOWED, ARENA_NONE = "full", "windowed", "none"
+
+    def ensure_arena(self, plan) -> str:
+        """Make room for the snapshot of `plan` in HBM.
+        "full": the arena covers the plan (the training stream then only waits for
+        the gather kernel).  "windowed": DLROVER_B200_ARENA_LIMIT_MB caps the arena
+        and the checkpoint is streamed through it window by window (blocking).
+        "none": HBM has no room for a second copy of the state — the caller saves
+        in place instead (DMA straight from the tensors)."""
+        end = plan.arena_end
+        if end <= self.ctx.arena_info()[1]:
+            return self.ARENA_FULL
         forced = int(os.getenv("DLROVER_B200_ARENA_LIMIT_MB", "0") or 0)
         if forced:
-            self.ctx.set_arena_limit(max(8, forced) << 20)
+            limit = max(8, forced) << 20
+            self.ctx.set_arena_limit(limit)
+            self.ctx.arena_reserve(min(end, limit))
+            return self.ARENA_FULL if end <= limit else self.ARENA_WINDOWED
         try:
             self.ctx.arena_reserve(end)
-            return
+            return self.ARENA_FULL
         except native.NativeError as e:
             if e.code != native.FC_ENOMEM:
                 raise
-        free, _ = torch.cuda.mem_get_info(self.device_index)
-        limit = max(64 << 20, min(end, free // 2))
-        logger.warning(
-            f"No room for a {end / 2**30:.1f} GiB snapshot arena in HBM ({free / 2**30:.1f} GiB "
-            f"free): streaming the checkpoint through a {limit / 2**30:.2f} GiB window; saves "
-            "block until the data is in shared memory.")
-        self.ctx.set_arena_limit(limit)
-        self.ctx.arena_reserve(limit)
+        if not self._warned_no_arena:
+            self._warned_no_arena = True
+            free, _ = torch.cuda.mem_get_info(self.device_index)
+            logger.warning(
+                f"No room for a {end / 2**30:.1f} GiB snapshot arena in HBM ({free / 2**30:.1f} "
+                "GiB free): checkpoints are drained in place (DMA straight from the tensors). "
+                "Saves block until the data is in shared memory unless the engine runs with "
+                "in_place=True and the optimizer is guarded (see README, 'in-place saves').")
+        return self.ARENA_NONE
 
     def close(self):
         for p in self._plans.values():
@@ -379,6 +389,9 @@ class SharedMemoryHandler:
         self.last_timings: Optional[Tuple[float, float, float]] = None
         # torch.cuda.Event recorded right after the last gather kernel
         self.last_pack_event = None
+        # in-place saves (no HBM snapshot): opt-in, see write_ranges
+        self.in_place = os.getenv("DLROVER_B200_IN_PLACE", "0") == "1"
+        self.last_save_in_place = False
         if not host:
             # a drain still in flight when the interpreter exits must finish (the
             # completion thread is a daemon): otherwise the last checkpoint of a
@@ -478,7 +491,8 @@ class SharedMemoryHandler:
                      stream=None, finish: Optional[Callable[[], None]] = None,
                      keepalive: Optional[list] = None,
                      pre_drain: Optional[Callable[[], None]] = None,
-                     on_error: Optional[Callable[[], None]] = None):
+                     on_error: Optional[Callable[[], None]] = None,
+                     in_place: Optional[bool] = None):
         """Move bytes into the (already sized) segment.
 
         device_ranges / host_ranges: (tensor, segment offset, nbytes) for CUDA /
@@ -486,6 +500,10 @@ class SharedMemoryHandler:
         one gather kernel + DMA drain, the rest is written by the host right
         away.  `finish` runs once everything has landed — inline when blocking,
         else on the completion thread of the returned PendingSave.
+        in_place (default: self.in_place): no snapshot — the drain reads the CUDA
+        tensors themselves, so they must not be written until the save is done
+        (wait_pending / PendingSave.wait).  Also chosen, together with blocking,
+        when HBM has no room for the snapshot arena.
         """
         keepalive = keepalive if keepalive is not None else []
         for chunk, off in raw_chunks:
@@ -516,16 +534,28 @@ class SharedMemoryHandler:
                 # stream wait for `last_pack_event` before it MUTATES the tensors
                 stream.wait_stream(current)
             plan = stager.plan_for(device_ranges, keepalive, role="save", stream=stream)
+            in_place = self.in_place if in_place is None else in_place
+            arena = stager.ARENA_NONE if in_place else stager.ensure_arena(plan)
+            if arena == stager.ARENA_NONE and not in_place:
+                # nobody promised to keep the tensors unchanged: drain before returning
+                in_place = blocking = True
             # bounded-arena saves drain inside save_async: announce first, inline
-            windowed = plan.arena_end > stager.ctx.arena_info()[1]
+            windowed = arena == stager.ARENA_WINDOWED
             hold = pre_drain is not None and not blocking and not windowed
             if pre_drain is not None and not hold:
                 pre_drain()
                 pre_drain = None
-            ticket = plan.save_async(self.shared_memory.address, stream, hold=hold)
-            ev = torch.cuda.Event()
-            ev.record(stream)
-            self.last_pack_event = ev
+            if in_place:
+                ticket = plan.save_direct_async(self.shared_memory.address, stream, hold=hold)
+            else:
+                ticket = plan.save_async(self.shared_memory.address, stream, hold=hold)
+            self.last_save_in_place = in_place
+            if in_place:
+                self.last_pack_event = None  # there is no snapshot to wait for, only the drain
+            else:
+                ev = torch.cuda.Event()
+                ev.record(stream)
+                self.last_pack_event = ev
             ctx = stager.ctx
         if ctx is None and pre_drain is not None:
             pre_drain()
@@ -543,6 +573,18 @@ class SharedMemoryHandler:
         threading.Thread(target=self._run_completion, args=(pending,), name="fc-drain",
                          daemon=True).start()
         return pending
+
+    def wait_snapshot(self, stream=None):
+        """Order the caller's next WRITE to the saved tensors after the last save
+        has read them: with a snapshot (default) `stream` (default: current) waits on
+        the GPU for the gather kernel; after an in-place save the host waits for the
+        drain.  Cheap no-op when nothing is pending."""
+        if self.last_save_in_place:
+            self.wait_pending()
+            return
+        ev = self.last_pack_event
+        if ev is not None:
+            (stream or torch.cuda.current_stream()).wait_event(ev)
 
     def save_state_dict(self, state_dict, blocking: bool = True, stream=None,
                         on_complete: Optional[Callable[[], None]] = None,
@@ -694,12 +736,26 @@ class SharedMemoryHandler:
                 plan = stager.plan_for(
                     [(t, m.offset, m.numel * m.element_size) for t, m in device_pairs], [],
                     role="restore", stream=stream)
-                plan.restore_async(self.shared_memory.address, stream)
-                stager.ctx.restore_wait()
-                fill, scatter, _ = stager.ctx.restore_timings()
-                stats["fill_ms"], stats["scatter_ms"] = fill, scatter
-                stats["device_bytes"] = float(plan.payload_bytes)
+                stats.update(self._run_restore(stager, plan, stream))
         return stats
+
+    DIRECT_RESTORE_MIN_SPAN = 1 << 20  # average span size from which in-place restore wins
+
+    def _run_restore(self, stager: _DeviceStager, plan, stream) -> Dict[str, float]:
+        """Few large spans: H2D DMA straight into the targets.  Many small ones: one
+        DMA per merged segment run into the arena + one scatter kernel.
+        DLROVER_B200_RESTORE=direct|arena overrides the choice."""
+        direct = plan.payload_bytes >= plan.n_spans * self.DIRECT_RESTORE_MIN_SPAN
+        forced = os.getenv("DLROVER_B200_RESTORE", "")
+        if forced in ("direct", "arena"):
+            direct = forced == "direct"
+        if not direct and stager.ensure_arena(plan) == stager.ARENA_NONE:
+            direct = True
+        plan.restore_async(self.shared_memory.address, stream, direct=direct)
+        stager.ctx.restore_wait()
+        fill, scatter, _ = stager.ctx.restore_timings()
+        return {"device_bytes": float(plan.payload_bytes), "fill_ms": fill, "scatter_ms": scatter,
+                "direct": float(direct)}
 
     def read_ranges(self, device_ranges, stream=None) -> Dict[str, float]:
         """Inverse of write_ranges for CUDA targets: (tensor, segment offset,
@@ -722,10 +778,7 @@ class SharedMemoryHandler:
         if stream is None:
             stream = torch.cuda.current_stream(stager.device_index)
         plan = stager.plan_for(device_ranges, [], role="restore", stream=stream)
-        plan.restore_async(self.shared_memory.address, stream)
-        stager.ctx.restore_wait()
-        fill, scatter, _ = stager.ctx.restore_timings()
-        return {"device_bytes": float(plan.payload_bytes), "fill_ms": fill, "scatter_ms": scatter}
+        return self._run_restore(stager, plan, stream)
 
     # -- queries ------------------------------------------------------------------------
     def no_checkpoint_state(self):

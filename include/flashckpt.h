@@ -116,6 +116,9 @@ int fc_plan_destroy(fc_plan* plan);
  * end offset (max arena_off+nbytes) */
 int fc_plan_info(const fc_plan* plan, uint64_t* payload_bytes, uint32_t* n_items,
                  uint32_t* n_runs, uint64_t* arena_end);
+/* number of source spans (input ranges merged where tensor address AND arena
+ * offset both continue): the DMA count of the in-place save / restore below */
+int fc_plan_spans(const fc_plan* plan, uint32_t* n_spans);
 
 /* ---- device kernels alone (tests, ncu, roofline) ------------------------- */
 
@@ -154,6 +157,19 @@ int fc_save_async(fc_plan* plan, void* host_base, void* compute_stream,
  * (In the bounded-arena mode the save is complete on return; release is a no-op.) */
 int fc_save_async_held(fc_plan* plan, void* host_base, void* compute_stream, uint64_t* ticket);
 int fc_save_release(fc_ctx* ctx, uint64_t ticket);
+/* In-place save, no snapshot and no arena: the drain DMAs every span straight
+ * from the source tensors into host_base+offset (paced like fc_save_async; small
+ * spans share a batch).  Nothing runs on `compute_stream` — the drain is only
+ * ordered after the work already queued there — so the exposed cost is the call
+ * itself, but the caller must keep the tensors UNCHANGED until fc_save_poll /
+ * fc_save_wait report the ticket drained (fc_save_pack_done answers the same for
+ * such a ticket).  For states that do not fit in HBM twice (weights + fp32 Adam
+ * moments of an 8B model: 112 GB): parameters and optimizer state are not written
+ * between two optimizer steps, so a guard in front of the next step is enough.
+ * hold != 0: as fc_save_async_held.  This is the asynchronous form of the
+ * reference's loop (ckpt_saver.py:198-231), which blocks for the same copies. */
+int fc_save_direct_async(fc_plan* plan, void* host_base, void* compute_stream, int hold,
+                         uint64_t* ticket);
 /* FC_OK when the pack kernel of `ticket` has finished (tensors may change). */
 int fc_save_pack_done(fc_ctx* ctx, uint64_t ticket);
 /* FC_OK when all bytes are in host memory, FC_ENOTREADY while pending. */
@@ -187,6 +203,11 @@ int fc_host_pack(void* dst_base, uint32_t n, const void* const* src, const uint6
 /* DMA host_base+offset -> arena on the copy stream, then scatter
  * arena -> tensors on `stream` (gated by an event).  Inverse of fc_save_async. */
 int fc_restore_async(fc_plan* plan, const void* host_base, void* stream);
+/* In-place restore: H2D DMA of every span straight into the target tensors (no
+ * arena, no scatter kernel); `stream` waits for the last copy.  Preferable for
+ * few large spans or when HBM has no room for the arena; fc_restore_wait /
+ * fc_restore_timings apply (scatter time = 0). */
+int fc_restore_direct_async(fc_plan* plan, const void* host_base, void* stream);
 int fc_restore_wait(fc_ctx* ctx);
 int fc_restore_timings(fc_ctx* ctx, float* fill_ms, float* scatter_ms, float* total_ms);
 

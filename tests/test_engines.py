@@ -287,3 +287,59 @@ def test_failed_drain_gives_the_lock_back(agent, tmp_path, monkeypatch):
     monkeypatch.setattr(engine._shm_handler.metadata, "set", real_set)
     assert engine.save_to_memory(2, {MODEL: sd}, {MODEL: str(tmp_path / "x.pt")}) is True
     engine.close()
+
+
+@pytest.mark.gpu
+def test_in_place_saves_with_a_guarded_optimizer(cuda_device, agent, tmp_path):
+    """engine.in_place + guard_optimizer: checkpoints are drained straight from the
+    live parameters / optimizer state while training continues; the step pre-hook
+    keeps optimizer.step() from overwriting them before the drain has read them.
+    Every checkpoint equals the state at its save point, and training itself is
+    unchanged (same final weights as a run without checkpoints)."""
+    def run(checkpoint):
+        torch.manual_seed(3)
+        model = torch.nn.Sequential(torch.nn.Linear(1024, 4096), torch.nn.ReLU(),
+                                    torch.nn.Linear(4096, 4096), torch.nn.ReLU(),
+                                    torch.nn.Linear(4096, 1024)).to(cuda_device)  # 100 MB fp32
+        opt = torch.optim.AdamW(model.parameters(), lr=1e-3)
+        x = torch.randn(64, 1024, device=cuda_device)
+        engine = hook = None
+        if checkpoint:
+            engine = FullCheckpointEngine(str(tmp_path), PosixDiskStorage(), async_drain=True)
+            engine.in_place = True
+            hook = engine.guard_optimizer(opt)
+        snapshots = {}
+        for step in range(1, 7):
+            model(x).square().mean().backward()
+            opt.step()
+            opt.zero_grad(set_to_none=True)
+            if checkpoint:
+                sd = {"model": model.state_dict(), "optim": opt.state_dict()}
+                want = {k: v.detach().clone() for k, v in model.state_dict().items()}
+                want_m = opt.state_dict()["state"][0]["exp_avg"].detach().clone()
+                ok = engine.save_to_memory(step, {MODEL: sd}, {MODEL: str(tmp_path / "x.pt")},
+                                           blocking=True)
+                assert ok and engine._shm_handler.last_save_in_place
+                snapshots[step] = (want, want_m)
+                if step in (2, 5):  # look at what landed, after the drain
+                    engine.wait_memory_save(60)
+                    got = engine.load()
+                    for k, v in want.items():
+                        assert torch.equal(got["model"][k], v.cpu()), (step, k)
+                    assert torch.equal(got["optim"]["state"][0]["exp_avg"], want_m.cpu())
+                    del got
+        if checkpoint:
+            hook.remove()
+            engine.wait_memory_save(60)
+            got = engine.load()
+            want, want_m = snapshots[6]
+            for k, v in want.items():
+                assert torch.equal(got["model"][k], v.cpu())
+            del got
+            engine.close()
+        return [p.detach().clone() for p in model.parameters()]
+
+    with_ckpt = run(True)
+    without = run(False)
+    for a, b in zip(with_ckpt, without):
+        assert torch.equal(a, b)

@@ -255,3 +255,59 @@ def test_bounded_arena_streams_window_by_window(cuda_device):
         assert torch.equal(a, b)
     plan.destroy()
     ctx.destroy()
+
+
+def test_in_place_save_and_restore(cuda_device):
+    """fc_save_direct_async / fc_restore_direct_async: no arena at all — the DMA
+    reads / writes the tensors themselves.  Same oracle image, ragged sizes, many
+    small spans sharing a batch, spans merged where tensor and segment addresses
+    both continue."""
+    ctx = native.get_context(0)
+    g = torch.Generator().manual_seed(21)
+    # one flat buffer cut into consecutive views (-> merged into ONE span) ...
+    flat = torch.randint(0, 256, (3 << 20,), dtype=torch.uint8, generator=g).cuda()
+    cuts = [0, 7, 4096, 1 << 20, (1 << 20) + 13, 3 << 20]
+    views = [flat[a:b] for a, b in zip(cuts, cuts[1:])]
+    # ... 300 small separate tensors, and a big one (several drain pieces)
+    small = [torch.randint(0, 256, (n,), dtype=torch.uint8, generator=g).cuda()
+             for n in ([1, 3, 4, 17, 255, 4097] * 50)]
+    big = torch.randint(0, 256, (70 << 20,), dtype=torch.uint8, generator=g).cuda()
+    leaves = views + small + [big, torch.empty(0, dtype=torch.uint8).cuda()]
+    offsets, off = [], 0
+    for t in leaves:
+        offsets.append(off)
+        off += t.numel()
+    total = off
+    want = oracle.pack_ranges([oracle.tensor_bytes(t) for t in leaves], offsets, total)
+    plan = ctx.plan([t.data_ptr() for t in leaves], offsets, [t.numel() for t in leaves])
+    assert plan.n_spans == 1 + len(small) + 1
+    host = torch.zeros(total, dtype=torch.uint8).pin_memory()
+    k0, m0 = ctx.launch_count()
+    ticket = plan.save_direct_async(host.data_ptr(), torch.cuda.current_stream())
+    ctx.save_wait(ticket)
+    k1, m1 = ctx.launch_count()
+    assert k1 == k0 and m1 - m0 >= plan.n_spans  # DMA only, no kernel
+    assert np.array_equal(host.numpy(), want)
+    assert ctx.save_pack_done(ticket)
+    # held variant: nothing lands before the release
+    host.zero_()
+    ticket = plan.save_direct_async(host.data_ptr(), torch.cuda.current_stream(), hold=True)
+    torch.cuda.synchronize()
+    assert not ctx.save_poll(ticket) and not ctx.save_pack_done(ticket)
+    assert not host.numpy().any()
+    ctx.save_release(ticket)
+    ctx.save_wait(ticket)
+    assert np.array_equal(host.numpy(), want)
+    # in-place restore
+    keep = [t.clone() for t in leaves]
+    flat.zero_()
+    big.zero_()
+    for t in small:
+        t.zero_()
+    plan.restore_async(host.data_ptr(), torch.cuda.current_stream(), direct=True)
+    ctx.restore_wait()
+    for t, k in zip(leaves, keep):
+        assert torch.equal(t, k)
+    fill_ms, scatter_ms, total_ms = ctx.restore_timings()
+    assert fill_ms > 0 and total_ms >= fill_ms
+    plan.destroy()
