@@ -101,7 +101,7 @@ struct FcRun {  // merged contiguous arena range (drain/fill DMA granularity)
   uint64_t len;
 };
 
-struct FcSpan {  // one source range, merged where tensor AND arena addresses continue
+struct FcSpan {  // one input range (a tensor's bytes), ascending arena offset
   uint64_t tptr;
   uint64_t off;
   uint64_t len;
@@ -1095,17 +1095,10 @@ static int plan_fill(fc_plan* p, uint32_t n, const void* const* dev_ptrs,
   p->h_all.swap(all);
   std::sort(spans.begin(), spans.end(),
             [](const FcSpan& a, const FcSpan& b) { return a.off < b.off; });
-  p->spans.clear();
-  for (const FcSpan& sp : spans) {
-    if (!p->spans.empty()) {
-      FcSpan& last = p->spans.back();
-      if (sp.off == last.off + last.len && sp.tptr == last.tptr + last.len) {
-        last.len += sp.len;
-        continue;
-      }
-    }
-    p->spans.push_back(sp);
-  }
+  // NOT merged even where tensor and arena addresses both continue: two tensors may
+  // sit in adjacent but separate device allocations, and a cudaMemcpy must not
+  // straddle allocations (kernels do not care, the copy API does).
+  p->spans.swap(spans);
   return FC_OK;
 }
 

@@ -116,8 +116,9 @@ int fc_plan_destroy(fc_plan* plan);
  * end offset (max arena_off+nbytes) */
 int fc_plan_info(const fc_plan* plan, uint64_t* payload_bytes, uint32_t* n_items,
                  uint32_t* n_runs, uint64_t* arena_end);
-/* number of source spans (input ranges merged where tensor address AND arena
- * offset both continue): the DMA count of the in-place save / restore below */
+/* number of source spans (= non-empty input ranges; never merged, a DMA must not
+ * straddle two device allocations): the minimum DMA count of the in-place save /
+ * restore below */
 int fc_plan_spans(const fc_plan* plan, uint32_t* n_spans);
 
 /* ---- device kernels alone (tests, ncu, roofline) ------------------------- */
