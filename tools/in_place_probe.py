@@ -58,6 +58,7 @@ def burn(n):
         c = torch.mm(c, b)
     return c
 
+burn(50)  # warm-up (cuBLAS init, clocks) before calibrating
 torch.cuda.synchronize()
 t0 = time.perf_counter()
 burn(50)
