@@ -69,6 +69,9 @@ _SIGNATURES = {
     "fc_save_async_held": (ctypes.c_int, [_vp, _vp, _vp, ctypes.POINTER(_u64)]),
     "fc_save_release": (ctypes.c_int, [_vp, _u64]),
     "fc_save_direct_async": (ctypes.c_int, [_vp, _vp, _vp, ctypes.c_int, ctypes.POINTER(_u64)]),
+    "fc_save_hybrid_async": (ctypes.c_int, [_vp, _vp, _vp, _u64, ctypes.c_int,
+                                            ctypes.POINTER(_u64)]),
+    "fc_save_sources_wait": (ctypes.c_int, [_vp, _u64]),
     "fc_restore_direct_async": (ctypes.c_int, [_vp, _vp, _vp]),
     "fc_plan_spans": (ctypes.c_int, [_vp, ctypes.POINTER(_u32)]),
     "fc_save_pack_done": (ctypes.c_int, [_vp, _u64]),
@@ -221,6 +224,17 @@ class Plan:
                "fc_save_direct_async")
         return ticket.value
 
+    def save_hybrid_async(self, host_ptr: int, cut: int, compute_stream=None,
+                          hold: bool = False) -> int:
+        """Tensors at segment offsets >= cut are snapshotted into the arena, the rest
+        is drained in place (first)."""
+        ticket = _u64()
+        _check(load_library().fc_save_hybrid_async(self.handle, host_ptr,
+                                                   _stream_ptr(compute_stream), int(cut),
+                                                   int(hold), ctypes.byref(ticket)),
+               "fc_save_hybrid_async")
+        return ticket.value
+
     def restore_async(self, host_ptr: int, stream=None, direct: bool = False):
         """direct=True: DMA straight into the target tensors (no arena, no kernel)."""
         lib = load_library()
@@ -338,6 +352,10 @@ class Context:
     def save_pack_done(self, ticket: int) -> bool:
         return _check(load_library().fc_save_pack_done(self.handle, ticket),
                       "fc_save_pack_done") == FC_OK
+
+    def save_sources_wait(self, ticket: int):
+        """Block until save `ticket` no longer reads the source tensors."""
+        _check(load_library().fc_save_sources_wait(self.handle, ticket), "fc_save_sources_wait")
 
     def save_poll(self, ticket: int) -> bool:
         return _check(load_library().fc_save_poll(self.handle, ticket), "fc_save_poll") == FC_OK

@@ -595,9 +595,11 @@ struct fc_ctx {
     std::vector<FcRun> runs;
     std::vector<FcSpan> spans;  // in-place save: DMA straight from the tensors
     bool direct = false;
+    uint64_t arena_base = 0;  // arena byte 0 holds this segment offset (hybrid: the cut)
     uint64_t ticket = 0;
   };
-  uint64_t direct_ticket = 0;  // last ticket saved in place (no snapshot: sources stay frozen)
+  uint64_t direct_ticket = 0;  // last ticket with an in-place part (sources frozen until drained)
+  uint64_t inplace_done_ticket = 0;  // last ticket whose in-place part has left the tensors
   uint64_t held_ticket = 0;  // the pump must not start the drain of this ticket yet
   std::deque<DrainJob> jobs;
   bool pump_stop = false;
@@ -650,13 +652,23 @@ static void pump_main(fc_ctx* c) {
           }
         }
       }
+      if (e == cudaSuccess && (batch_bytes || batch_n)) {
+        e = cudaEventRecord(c->ring[0], c->copy_stream);
+        if (e == cudaSuccess) e = cudaEventSynchronize(c->ring[0]);
+      }
+      {
+        // the tensors are free again (on error too: nothing reads them any more)
+        std::lock_guard<std::mutex> lk(c->mu);
+        c->inplace_done_ticket = job.ticket;
+      }
+      c->cv.notify_all();
     }
     for (const FcRun& r : job.runs) {
       for (uint64_t o = 0; o < r.len && e == cudaSuccess; o += c->drain_piece) {
         const uint64_t len = std::min<uint64_t>(c->drain_piece, r.len - o);
         if (k >= (uint64_t)depth) e = cudaEventSynchronize(c->ring[k % depth]);  // piece k-depth
         if (e == cudaSuccess)
-          e = cudaMemcpyAsync(job.host + r.off + o, c->arena + r.off + o, len,
+          e = cudaMemcpyAsync(job.host + r.off + o, c->arena + (r.off - job.arena_base) + o, len,
                               cudaMemcpyDeviceToHost, c->copy_stream);
         if (e == cudaSuccess) e = cudaEventRecord(c->ring[k % depth], c->copy_stream);
         ++k;
@@ -1467,20 +1479,41 @@ static int save_async_impl(fc_plan* p, void* host_base, void* compute_stream, ui
   return FC_OK;
 }
 
-extern "C" int fc_save_direct_async(fc_plan* p, void* host_base, void* compute_stream, int hold,
-                                    uint64_t* ticket) {
+// In-place part below `cut` (DMA from the tensors, drained first), snapshot part at
+// and above it (LSU gather over a slice of the offset-sorted table into the arena,
+// whose byte 0 stands for segment offset `cut`).
+static int save_hybrid_impl(fc_plan* p, void* host_base, void* compute_stream, uint64_t cut,
+                            int hold, uint64_t* ticket) {
   if (!p || (!host_base && p->payload))
-    return fail(FC_EINVAL, "fc_save_direct_async: null argument%s%s");
+    return fail(FC_EINVAL, "fc_save_hybrid_async: null argument%s%s");
   fc_ctx* c = p->ctx;
   FC_GUARD(c);
   int rc = refresh_inflight(c);
   if (rc) return rc;
   if (c->save_inflight || c->restore_inflight)
-    return fail(FC_EBUSY, "fc_save_direct_async: previous save/restore still draining%s%s");
+    return fail(FC_EBUSY, "fc_save_hybrid_async: previous save/restore still draining%s%s");
   cudaStream_t cs = (cudaStream_t)compute_stream;
-  // no kernel: the pair of events orders the drain after everything already
-  // queued on the training stream (the optimizer step that produced the values)
+  const std::vector<FcItem>& it = p->h_all;
+  uint32_t n = (uint32_t)it.size();
+  uint32_t i0 = (uint32_t)(std::lower_bound(it.begin(), it.end(), cut,
+                                            [](const FcItem& a, uint64_t v) { return a.aoff < v; }) -
+                           it.begin());
+  if (i0 > 0 && it[i0 - 1].aoff + it[i0 - 1].nbytes > cut)
+    return fail(FC_EINVAL, "fc_save_hybrid_async: cut is not a tensor boundary%s%s");
+  if (i0 < n && p->arena_end - cut > c->arena_bytes)
+    return fail(FC_EINVAL, "fc_save_hybrid_async: arena smaller than the snapshot part%s%s");
+  // with no kernel the pair of events still orders the drain after everything
+  // already queued on the training stream (the optimizer step that produced the values)
   FC_CUDA(cudaEventRecord(c->ev_pack_start, cs));
+  if (i0 < n) {
+    FC_CUDA(cudaStreamWaitEvent(cs, p->ev_upload, 0));
+    uint32_t m = n - i0;
+    uint32_t grid = std::min<uint32_t>(m, (uint32_t)(c->sm_count * c->lsu_ctas_per_sm));
+    fc_copy_lsu<0><<<grid, kLsuThreads, 0, cs>>>(p->all.dev + i0, m, c->arena - cut);
+    FC_CUDA(cudaGetLastError());
+    c->n_kernels += 1;
+    FC_CUDA(cudaEventRecord(p->ev_last_use, cs));
+  }
   FC_CUDA(cudaEventRecord(c->ev_pack_end, cs));
   {
     std::lock_guard<std::mutex> lk(c->mu);
@@ -1489,8 +1522,14 @@ extern "C" int fc_save_direct_async(fc_plan* p, void* host_base, void* compute_s
     c->ticket += 1;
     fc_ctx::DrainJob job;
     job.host = static_cast<uint8_t*>(host_base);
-    job.spans = p->spans;
+    for (const FcSpan& sp : p->spans)
+      if (sp.off < cut) job.spans.push_back(sp);
+    for (const FcRun& r : p->runs) {
+      uint64_t a = std::max(r.off, cut), b = r.off + r.len;
+      if (b > a) job.runs.push_back({a, b - a});
+    }
     job.direct = true;
+    job.arena_base = cut;
     job.ticket = c->ticket;
     if (hold) c->held_ticket = c->ticket;
     c->direct_ticket = c->ticket;
@@ -1500,6 +1539,16 @@ extern "C" int fc_save_direct_async(fc_plan* p, void* host_base, void* compute_s
   }
   c->cv.notify_all();
   return FC_OK;
+}
+
+extern "C" int fc_save_hybrid_async(fc_plan* p, void* host_base, void* compute_stream,
+                                    uint64_t cut, int hold, uint64_t* ticket) {
+  return save_hybrid_impl(p, host_base, compute_stream, cut, hold, ticket);
+}
+
+extern "C" int fc_save_direct_async(fc_plan* p, void* host_base, void* compute_stream, int hold,
+                                    uint64_t* ticket) {
+  return save_hybrid_impl(p, host_base, compute_stream, ~0ull, hold, ticket);
 }
 
 extern "C" int fc_restore_direct_async(fc_plan* p, const void* host_base, void* stream) {
@@ -1539,15 +1588,36 @@ static int check_ticket(fc_ctx* c, uint64_t ticket, const char* who) {
 
 static int drain_status(fc_ctx* c, uint64_t ticket, bool wait);
 
+// FC_OK once nothing of save `ticket` reads the source tensors any more: its gather
+// kernel (if any) has finished and its in-place part (if any) has been drained.
+static int sources_status(fc_ctx* c, uint64_t ticket, bool wait) {
+  {
+    std::unique_lock<std::mutex> lk(c->mu);
+    if (ticket == c->direct_ticket) {
+      if (wait)
+        c->cv.wait(lk, [&] { return c->inplace_done_ticket >= ticket || c->drain_rc != FC_OK; });
+      if (c->drain_rc != FC_OK) return fail(c->drain_rc, "%s", c->drain_err.c_str());
+      if (c->inplace_done_ticket < ticket) return FC_ENOTREADY;
+    }
+  }
+  DeviceGuard g(c->device);
+  if (!g.ok) return fail(FC_ECUDA, "cudaSetDevice failed%s%s");
+  cudaError_t e = wait ? cudaEventSynchronize(c->ev_pack_end) : cudaEventQuery(c->ev_pack_end);
+  if (e == cudaSuccess) return FC_OK;
+  if (e == cudaErrorNotReady) return FC_ENOTREADY;
+  return fail(FC_ECUDA, "cudaEvent(pack): %s", cudaGetErrorString(e));
+}
+
 extern "C" int fc_save_pack_done(fc_ctx* c, uint64_t ticket) {
   int rc = check_ticket(c, ticket, "fc_save_pack_done");
   if (rc) return rc;
-  if (ticket == c->direct_ticket) return drain_status(c, ticket, false);  // no snapshot was taken
-  FC_GUARD(c);
-  cudaError_t e = cudaEventQuery(c->ev_pack_end);
-  if (e == cudaSuccess) return FC_OK;
-  if (e == cudaErrorNotReady) return FC_ENOTREADY;
-  return fail(FC_ECUDA, "cudaEventQuery(pack): %s", cudaGetErrorString(e));
+  return sources_status(c, ticket, false);
+}
+
+extern "C" int fc_save_sources_wait(fc_ctx* c, uint64_t ticket) {
+  int rc = check_ticket(c, ticket, "fc_save_sources_wait");
+  if (rc) return rc;
+  return sources_status(c, ticket, true);
 }
 
 static int drain_status(fc_ctx* c, uint64_t ticket, bool wait) {

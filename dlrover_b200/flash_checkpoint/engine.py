@@ -343,6 +343,17 @@ class CheckpointEngine(metaclass=ABCMeta):
     def in_place(self, value: bool):
         self._shm_handler.in_place = bool(value)
 
+    @property
+    def in_place_snapshot_bytes(self) -> int:
+        """HBM an in-place save may spend on snapshotting the tail of the state; the
+        rest is drained in place first, so wait_snapshot() returns sooner
+        (default 0; DLROVER_B200_IN_PLACE_SNAPSHOT_MB)."""
+        return self._shm_handler.in_place_snapshot_bytes
+
+    @in_place_snapshot_bytes.setter
+    def in_place_snapshot_bytes(self, value: int):
+        self._shm_handler.in_place_snapshot_bytes = int(value)
+
     def wait_snapshot(self):
         """Call before the first write to tensors handed to the last save."""
         self._shm_handler.wait_snapshot()

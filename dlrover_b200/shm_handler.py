@@ -391,7 +391,12 @@ class SharedMemoryHandler:
         self.last_pack_event = None
         # in-place saves (no HBM snapshot): opt-in, see write_ranges
         self.in_place = os.getenv("DLROVER_B200_IN_PLACE", "0") == "1"
+        # HBM an in-place save may spend on snapshotting the tail of the state (the rest
+        # is drained in place first): shortens the time the tensors stay frozen
+        self.in_place_snapshot_bytes = int(os.getenv("DLROVER_B200_IN_PLACE_SNAPSHOT_MB", "0")) << 20
         self.last_save_in_place = False
+        self.last_hybrid_cut = None
+        self._last_ticket = None
         if not host:
             # a drain still in flight when the interpreter exits must finish (the
             # completion thread is a daemon): otherwise the last checkpoint of a
@@ -535,7 +540,14 @@ class SharedMemoryHandler:
                 stream.wait_stream(current)
             plan = stager.plan_for(device_ranges, keepalive, role="save", stream=stream)
             in_place = self.in_place if in_place is None else in_place
-            arena = stager.ARENA_NONE if in_place else stager.ensure_arena(plan)
+            cut = None  # hybrid: segment offset from which the tensors are snapshotted
+            if in_place:
+                arena = stager.ARENA_NONE
+                cut = self._hybrid_cut(stager, plan, device_ranges)
+                if cut is not None and cut <= min(r[1] for r in device_ranges):
+                    in_place, cut, arena = False, None, stager.ARENA_FULL  # everything fits
+            else:
+                arena = stager.ensure_arena(plan)
             if arena == stager.ARENA_NONE and not in_place:
                 # nobody promised to keep the tensors unchanged: drain before returning
                 in_place = blocking = True
@@ -545,10 +557,14 @@ class SharedMemoryHandler:
             if pre_drain is not None and not hold:
                 pre_drain()
                 pre_drain = None
-            if in_place:
+            if in_place and cut is not None:
+                ticket = plan.save_hybrid_async(self.shared_memory.address, cut, stream, hold=hold)
+            elif in_place:
                 ticket = plan.save_direct_async(self.shared_memory.address, stream, hold=hold)
             else:
                 ticket = plan.save_async(self.shared_memory.address, stream, hold=hold)
+            self._last_ticket = (stager.ctx, ticket)
+            self.last_hybrid_cut = cut
             self.last_save_in_place = in_place
             if in_place:
                 self.last_pack_event = None  # there is no snapshot to wait for, only the drain
@@ -574,12 +590,40 @@ class SharedMemoryHandler:
                          daemon=True).start()
         return pending
 
+    def _hybrid_cut(self, stager: _DeviceStager, plan, device_ranges) -> Optional[int]:
+        """In-place save with a snapshot budget: the segment offset from which the
+        tensors fit into the arena (None: no budget / no arena -> pure in-place)."""
+        budget = self.in_place_snapshot_bytes
+        if budget <= 0:
+            return None
+        want = min(budget, plan.arena_end)
+        try:
+            if stager.ctx.arena_info()[1] < want:
+                stager.ctx.arena_reserve(want)
+        except native.NativeError as e:
+            if e.code != native.FC_ENOMEM:
+                raise
+        cap = min(stager.ctx.arena_info()[1], budget)
+        end, cut = plan.arena_end, None
+        for _, off, _ in sorted(device_ranges, key=lambda r: r[1], reverse=True):
+            if end - off > cap:
+                break
+            cut = off
+        return cut
+
     def wait_snapshot(self, stream=None):
         """Order the caller's next WRITE to the saved tensors after the last save
         has read them: with a snapshot (default) `stream` (default: current) waits on
         the GPU for the gather kernel; after an in-place save the host waits for the
         drain.  Cheap no-op when nothing is pending."""
         if self.last_save_in_place:
+            if self._last_ticket is not None and self.pending_save() is not None:
+                ctx, ticket = self._last_ticket
+                try:
+                    ctx.save_sources_wait(ticket)  # in-place part drained (+ gather done)
+                    return
+                except native.NativeError:
+                    pass  # a later ticket took over / drain error: fall through
             self.wait_pending()
             return
         ev = self.last_pack_event

@@ -171,8 +171,19 @@ int fc_save_release(fc_ctx* ctx, uint64_t ticket);
  * reference's loop (ckpt_saver.py:198-231), which blocks for the same copies. */
 int fc_save_direct_async(fc_plan* plan, void* host_base, void* compute_stream, int hold,
                          uint64_t* ticket);
-/* FC_OK when the pack kernel of `ticket` has finished (tensors may change). */
+/* Hybrid of the two: tensors whose segment offset is >= `cut` (a tensor boundary)
+ * are snapshotted into the arena (which must hold arena_end - cut bytes; its byte 0
+ * stands for offset `cut`), the tensors below `cut` are drained in place — first, so
+ * that they are released as early as possible.  Spends whatever HBM is to spare on
+ * shortening the time the sources stay frozen: (bytes below cut) / PCIe rate. */
+int fc_save_hybrid_async(fc_plan* plan, void* host_base, void* compute_stream, uint64_t cut,
+                         int hold, uint64_t* ticket);
+/* FC_OK once nothing of save `ticket` reads the source tensors any more (they may
+ * change): its gather kernel, if any, has finished and its in-place part, if any,
+ * has been drained; FC_ENOTREADY before.  fc_save_sources_wait blocks the calling
+ * host thread until then. */
 int fc_save_pack_done(fc_ctx* ctx, uint64_t ticket);
+int fc_save_sources_wait(fc_ctx* ctx, uint64_t ticket);
 /* FC_OK when all bytes are in host memory, FC_ENOTREADY while pending. */
 int fc_save_poll(fc_ctx* ctx, uint64_t ticket);
 int fc_save_wait(fc_ctx* ctx, uint64_t ticket);

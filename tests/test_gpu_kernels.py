@@ -310,3 +310,50 @@ def test_in_place_save_and_restore(cuda_device):
     fill_ms, scatter_ms, total_ms = ctx.restore_timings()
     assert fill_ms > 0 and total_ms >= fill_ms
     plan.destroy()
+
+
+def test_hybrid_save_snapshot_tail_in_place_head(cuda_device):
+    """fc_save_hybrid_async: tensors at offsets >= cut go through the arena (LSU gather
+    over a table slice, arena byte 0 = offset cut), the rest is drained in place first;
+    fc_save_pack_done / fc_save_sources_wait tell when the tensors may change."""
+    ctx = native.get_context(0)
+    g = torch.Generator().manual_seed(31)
+    sizes = [5, 4096, 1 << 20, 3, (2 << 20) + 7, 17, 40 << 20, 1, 300_001, 9 << 20]
+    leaves = [torch.randint(0, 256, (n,), dtype=torch.uint8, generator=g).cuda() for n in sizes]
+    offsets, off = [], 0
+    for t in leaves:
+        offsets.append(off)
+        off += t.numel()
+    total = off
+    want = oracle.pack_ranges([oracle.tensor_bytes(t) for t in leaves], offsets, total)
+    plan = ctx.plan([t.data_ptr() for t in leaves], offsets, sizes)
+    host = torch.zeros(total, dtype=torch.uint8).pin_memory()
+    stream = torch.cuda.current_stream()
+    for first_snapshotted in (0, 4, 7, len(leaves)):   # all snapshot ... all in place
+        cut = offsets[first_snapshotted] if first_snapshotted < len(leaves) else total
+        ctx.arena_reserve(max(total - cut, 8))
+        host.zero_()
+        k0, m0 = ctx.launch_count()
+        ticket = plan.save_hybrid_async(host.data_ptr(), cut, stream, hold=True)
+        torch.cuda.synchronize()
+        # held: the in-place part has not been read yet -> the tensors are not free
+        if first_snapshotted > 0:
+            assert not ctx.save_pack_done(ticket)
+        assert not host.numpy().any()
+        ctx.save_release(ticket)
+        ctx.save_sources_wait(ticket)
+        assert ctx.save_pack_done(ticket)
+        # from here on the sources may change without touching the checkpoint
+        keep = [t.clone() for t in leaves]
+        for t in leaves[first_snapshotted:]:
+            t.add_(1)
+        ctx.save_wait(ticket)
+        k1, m1 = ctx.launch_count()
+        assert k1 - k0 == (1 if first_snapshotted < len(leaves) else 0)
+        assert np.array_equal(host.numpy(), want), first_snapshotted
+        for t, k in zip(leaves, keep):
+            t.copy_(k)
+    # a cut inside a tensor, or an arena smaller than the snapshot part, is refused
+    with pytest.raises(native.NativeError):
+        plan.save_hybrid_async(host.data_ptr(), offsets[2] + 1, stream)
+    plan.destroy()

@@ -7,6 +7,9 @@ Modes (one process each, PROBE_MODE):
   fallback   default engine, arena allocation fails -> in-place drain, blocking
   in_place   engine.in_place=True + guarded "optimizer": the drain overlaps the next
              forward/backward; only optimizer.step() waits for it
+  hybrid     in_place + engine.in_place_snapshot_bytes (PROBE_SNAPSHOT_GB, default 32): the
+             tail of the state is snapshotted into spare HBM, the head is drained in place
+             first; optimizer.step() only waits for the head
 Synthetic step: PROBE_STEP_MS of bf16 matmuls (forward/backward: reads the parameters
 only), then the "optimizer step" (guard, then an in-place update of one parameter), then a
 loss.item()-style host read.  stall = (loop wall time with checkpoints - without) / saves.
@@ -68,8 +71,11 @@ inner = max(1, int(step_ms / 1e3 / per_mm))
 
 ckpt = DdpCheckpointer(f"/tmp/fc_ipprobe_{os.getenv('TORCHELASTIC_RUN_ID')}")
 engine = ckpt.engine
-if mode == "in_place":
+if mode in ("in_place", "hybrid"):
     engine.in_place = True
+if mode == "hybrid":
+    # spend part of the free HBM on a snapshot of the tail of the state
+    engine.in_place_snapshot_bytes = int(float(os.getenv("PROBE_SNAPSHOT_GB", "32")) * 1e9)
 first = next(iter(params.values()))
 
 
@@ -117,7 +123,8 @@ ok = bool(torch.equal(loaded["optimizer"]["state"][idx]["exp_avg"],
 del loaded
 print(json.dumps({
     "mode": mode, "state_GB": round(S / 1e9, 2), "free_hbm_GB_before_saves": round(free_after / 1e9, 1),
-    "in_place_used": bool(handler.last_save_in_place), "train_step_ms": round(base / (every * rounds) * 1e3, 1),
+    "in_place_used": bool(handler.last_save_in_place),
+    "hybrid_cut_GB": None if handler.last_hybrid_cut is None else round(handler.last_hybrid_cut / 1e9, 2), "train_step_ms": round(base / (every * rounds) * 1e3, 1),
     "saves": n, "stall_ms_per_save": round((with_ckpt - base) / max(n, 1) * 1e3, 1),
     "save_call_ms": round(call_s / max(n, 1) * 1e3, 1),
     "drain_ms": round(timings[1], 1) if timings else None,
