@@ -128,6 +128,7 @@ class DeepSpeedCheckpointer(Checkpointer):
 
     def save_checkpoint(self, save_dir, tag=None, client_state={}, save_latest=True,
                         storage_type=StorageType.DISK):
+        self._async_save_engine.guard_if_in_place(getattr(self.engine, "optimizer", None))
         if storage_type == StorageType.MEMORY:
             sd, paths = self._capture(save_dir, tag, client_state, save_latest)
             self._async_save_engine.save_to_memory(tag, sd, paths)

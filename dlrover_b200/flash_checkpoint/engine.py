@@ -133,6 +133,26 @@ def timer(func):
     return wrapper
 
 
+def _torch_optimizers(obj, depth=0):
+    """The torch.optim.Optimizer objects under a (possibly wrapped) optimizer."""
+    if obj is None or depth > 4:
+        return
+    if hasattr(obj, "register_step_pre_hook"):
+        yield obj
+        return
+    for attr in ("optimizer", "base_optimizer"):
+        inner = getattr(obj, attr, None)
+        if inner is not None and inner is not obj:
+            yield from _torch_optimizers(inner, depth + 1)
+            return
+    for attr in ("chained_optimizers", "optimizers"):
+        inner = getattr(obj, attr, None)
+        if isinstance(inner, (list, tuple)):
+            for o in inner:
+                yield from _torch_optimizers(o, depth + 1)
+            return
+
+
 def start_async_save():
     """Body of the stand-alone saver daemon.  It owns the segments like an agent
     does, but nobody outlives it to use them (the meta tree lives in this process):
@@ -360,9 +380,24 @@ class CheckpointEngine(metaclass=ABCMeta):
 
     def guard_optimizer(self, optimizer):
         """Make `optimizer.step()` wait until the last save no longer reads the
-        parameters / optimizer state (torch.optim step pre-hook).  Returns the
-        hook handle."""
-        return optimizer.register_step_pre_hook(lambda *_a, **_k: self.wait_snapshot())
+        parameters / optimizer state (torch.optim step pre-hook).  Framework wrappers
+        (Megatron's optimizers, DeepSpeed's ZeRO optimizers) are unwrapped down to the
+        torch optimizers whose step() does the writing.  Idempotent; returns the list of
+        new hook handles."""
+        guarded = self.__dict__.setdefault("_guarded_optimizers", set())
+        handles = []
+        for opt in _torch_optimizers(optimizer):
+            if id(opt) in guarded:
+                continue
+            guarded.add(id(opt))
+            handles.append(opt.register_step_pre_hook(lambda *_a, **_k: self.wait_snapshot()))
+        return handles
+
+    def guard_if_in_place(self, optimizer):
+        """Checkpointers that are handed the optimizer call this on every save: with
+        in-place saves switched on, the optimizer is guarded automatically."""
+        if self.in_place and optimizer is not None:
+            self.guard_optimizer(optimizer)
 
     def save_state_dict_to_memory(self, state_dict, conf: CheckpointConfig, blocking=False):
         """Returns True when the state dict was (or is being) written to shared

@@ -64,6 +64,7 @@ class FsdpShardCheckpointer(Checkpointer):
 
     def save_checkpoint(self, step, model, optimizer, extra_sd={}, path="",
                         storage_type=StorageType.DISK):
+        self._engine.guard_if_in_place(optimizer)
         with FSDP.state_dict_type(model, StateDictType.SHARDED_STATE_DICT):
             state_dict = {"model": model.state_dict(),
                           "optim": FSDP.optim_state_dict(model, optimizer)}
@@ -127,6 +128,7 @@ class FsdpFullCheckpointer(Checkpointer):
                         storage_type=StorageType.DISK):
         if path == "":
             path = os.path.join(self.checkpoint_dir, f"{step}/rank_{self._rank}.pt")
+        self._engine.guard_if_in_place(optimizer)
         with self._full_state(model):
             state_dict = {"model": model.state_dict(),
                           "optimizer": FSDP.optim_state_dict(model, optimizer)}

@@ -139,6 +139,7 @@ def save_checkpoint(iteration, model, optimizer, opt_param_scheduler,
     finally:
         if _get_rank() == 0:
             saver.update_tracer_file(iteration)
+    saver.engine.guard_if_in_place(optimizer)
     if storage_type == StorageType.MEMORY:
         saver.engine.save_to_memory(iteration, saver.state_dict, saver.paths)
     else:

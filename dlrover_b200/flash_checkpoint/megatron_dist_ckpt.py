@@ -257,6 +257,7 @@ def save_checkpoint(iteration, model, optimizer, opt_param_scheduler,
     if shard_state:
         state_dicts[_OPTIM] = shard_state
         paths[_OPTIM] = get_dist_optimizer_checkpoint_name(args.save, iteration)
+    checkpointer.engine.guard_if_in_place(optimizer)
     if storage_type == StorageType.MEMORY:
         checkpointer.engine.save_to_memory(iteration, state_dicts, paths)
     else:

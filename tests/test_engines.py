@@ -343,3 +343,35 @@ def test_in_place_saves_with_a_guarded_optimizer(cuda_device, agent, tmp_path):
     without = run(False)
     for a, b in zip(with_ckpt, without):
         assert torch.equal(a, b)
+
+
+def test_guard_optimizer_unwraps_framework_optimizers(agent, tmp_path):
+    """guard_optimizer reaches the torch optimizers under Megatron-/DeepSpeed-style
+    wrappers, is idempotent, and guard_if_in_place only acts when in-place saves are on."""
+    engine = FullCheckpointEngine(str(tmp_path), PosixDiskStorage(), async_drain=False)
+    a = torch.optim.SGD([torch.nn.Parameter(torch.zeros(2))], lr=0.1)
+    b = torch.optim.SGD([torch.nn.Parameter(torch.zeros(2))], lr=0.1)
+
+    class Wrapped:           # e.g. Float16OptimizerWithFloat16Params / DeepSpeedZeroOptimizer
+        def __init__(self, inner):
+            self.optimizer = inner
+
+    class Chained:           # e.g. megatron ChainedOptimizer
+        def __init__(self, *inner):
+            self.chained_optimizers = list(inner)
+
+    engine.guard_if_in_place(a)
+    assert not a._optimizer_step_pre_hooks      # in_place is off: nothing registered
+    engine.in_place = True
+    calls = []
+    engine.wait_snapshot = lambda: calls.append(1)
+    handles = engine.guard_optimizer(Chained(Wrapped(a), b))
+    assert len(handles) == 2
+    assert engine.guard_optimizer(Wrapped(a)) == []   # already guarded
+    for p in a.param_groups[0]["params"]:
+        p.grad = torch.ones(2)
+    a.step()
+    assert calls == [1]
+    engine.guard_if_in_place(b)
+    assert len(b._optimizer_step_pre_hooks) == 1
+    engine.close()
