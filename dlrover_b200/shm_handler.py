@@ -544,7 +544,8 @@ class SharedMemoryHandler:
             if in_place:
                 arena = stager.ARENA_NONE
                 cut = self._hybrid_cut(stager, plan, device_ranges)
-                if cut is not None and cut <= min(r[1] for r in device_ranges):
+                if cut is not None and cut <= min(r[1] for r in device_ranges) \
+                        and stager.ensure_arena(plan) == stager.ARENA_FULL:
                     in_place, cut, arena = False, None, stager.ARENA_FULL  # everything fits
             else:
                 arena = stager.ensure_arena(plan)
