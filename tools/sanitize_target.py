@@ -38,4 +38,23 @@ for variant in (native.VARIANT_TMA, native.VARIANT_LSU):
     ctx.restore_wait()
     for a, b in zip(tensors, keep):
         assert torch.equal(a, b)
+# hybrid / in-place saves: LSU gather over a table slice into an arena whose byte 0
+# stands for the cut offset; in-place restore
+ctx.set_variant(native.VARIANT_AUTO)
+for first in (0, 3, 6, len(tensors)):
+    cut = offs[first] if first < len(tensors) else o
+    host.zero_()
+    tk = plan.save_hybrid_async(host.data_ptr(), cut, torch.cuda.current_stream())
+    ctx.save_sources_wait(tk)
+    ctx.save_wait(tk)
+    img = host.numpy()
+    for t, off in zip(tensors, offs):
+        assert np.array_equal(img[off:off + t.numel()], t.cpu().numpy())
+keep = [t.clone() for t in tensors]
+for t in tensors:
+    t.zero_()
+plan.restore_async(host.data_ptr(), torch.cuda.current_stream(), direct=True)
+ctx.restore_wait()
+for a, b in zip(tensors, keep):
+    assert torch.equal(a, b)
 print("SANITIZE_TARGET_OK")
