@@ -194,8 +194,6 @@ def run_reference(args):
         dt = time.perf_counter() - t0
         # restore the reference's way: CPU views on the (pageable) segment, one
         # H2D copy_ per tensor (ckpt_saver.py:144-161 + model.load_state_dict)
-        from oracle import shm_layout
-
         views = shm_layout_read(saver)
         torch.cuda.synchronize()
         r0 = time.perf_counter()
@@ -522,8 +520,9 @@ def measure_stall(ckpt, sd, S, dev, world):
 
 
 def measure_restore(ckpt, sd, S, world):
-    """In-memory restore of the shard: ours = DMA fill of the arena + scatter
-    kernel into the live tensors (load_checkpoint_into); reference style =
+    """In-memory restore of the shard: ours = load_checkpoint_into (H2D DMA from the
+    pinned segment straight into the live tensors for few large ones, arena + scatter
+    kernel for many small ones); reference style =
     load_checkpoint() (CPU views on the segment) + per-tensor copy_ to the
     device, which is what model.load_state_dict does."""
     import torch
