@@ -303,11 +303,12 @@ def test_in_place_saves_with_a_guarded_optimizer(cuda_device, agent, tmp_path):
                                     torch.nn.Linear(4096, 1024)).to(cuda_device)  # 100 MB fp32
         opt = torch.optim.AdamW(model.parameters(), lr=1e-3)
         x = torch.randn(64, 1024, device=cuda_device)
-        engine = hook = None
+        engine, hooks = None, []
         if checkpoint:
             engine = FullCheckpointEngine(str(tmp_path), PosixDiskStorage(), async_drain=True)
             engine.in_place = True
-            hook = engine.guard_optimizer(opt)
+            hooks = engine.guard_optimizer(opt)
+            assert len(hooks) == 1
         snapshots = {}
         for step in range(1, 7):
             model(x).square().mean().backward()
@@ -329,7 +330,8 @@ def test_in_place_saves_with_a_guarded_optimizer(cuda_device, agent, tmp_path):
                     assert torch.equal(got["optim"]["state"][0]["exp_avg"], want_m.cpu())
                     del got
         if checkpoint:
-            hook.remove()
+            for h in hooks:
+                h.remove()
             engine.wait_memory_save(60)
             got = engine.load()
             want, want_m = snapshots[6]
