@@ -537,7 +537,8 @@ def measure_restore(ckpt, sd, S, world):
     torch.cuda.synchronize()
     ours = time.perf_counter() - t0
     ok = step > 0 and all(torch.equal(sd[k], p) for k, p in zip((keys[0], keys[7], keys[-1]), probe))
-    out = {"ours_ms": ours * 1e3, "ours_GBps": S / ours / 1e9, "bit_exact_spot_check": bool(ok)}
+    out = {"ours_ms": ours * 1e3, "ours_GBps": S / ours / 1e9, "bit_exact_spot_check": bool(ok),
+           "device_times": dict(ckpt.engine._shm_handler.last_restore_stats)}
     if world == 1:
         barrier_sync(world)
         t0 = time.perf_counter()

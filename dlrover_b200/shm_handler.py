@@ -395,6 +395,7 @@ class SharedMemoryHandler:
         # is drained in place first): shortens the time the tensors stay frozen
         self.in_place_snapshot_bytes = int(os.getenv("DLROVER_B200_IN_PLACE_SNAPSHOT_MB", "0")) << 20
         self.last_save_in_place = False
+        self.last_restore_stats: Dict[str, float] = {}
         self.last_hybrid_cut = None
         self._last_ticket = None
         if not host:
@@ -799,8 +800,9 @@ class SharedMemoryHandler:
         plan.restore_async(self.shared_memory.address, stream, direct=direct)
         stager.ctx.restore_wait()
         fill, scatter, _ = stager.ctx.restore_timings()
-        return {"device_bytes": float(plan.payload_bytes), "fill_ms": fill, "scatter_ms": scatter,
-                "direct": float(direct)}
+        self.last_restore_stats = {"device_bytes": float(plan.payload_bytes), "fill_ms": fill,
+                                   "scatter_ms": scatter, "direct": float(direct)}
+        return dict(self.last_restore_stats)
 
     def read_ranges(self, device_ranges, stream=None) -> Dict[str, float]:
         """Inverse of write_ranges for CUDA targets: (tensor, segment offset,
