@@ -68,6 +68,7 @@ _SIGNATURES = {
     "fc_save_async": (ctypes.c_int, [_vp, _vp, _vp, ctypes.POINTER(_u64)]),
     "fc_save_async_held": (ctypes.c_int, [_vp, _vp, _vp, ctypes.POINTER(_u64)]),
     "fc_save_release": (ctypes.c_int, [_vp, _u64]),
+    "fc_save_cancel": (ctypes.c_int, [_vp, _u64]),
     "fc_save_direct_async": (ctypes.c_int, [_vp, _vp, _vp, ctypes.c_int, ctypes.POINTER(_u64)]),
     "fc_save_hybrid_async": (ctypes.c_int, [_vp, _vp, _vp, _u64, ctypes.c_int,
                                             ctypes.POINTER(_u64)]),
@@ -352,6 +353,15 @@ class Context:
     def save_pack_done(self, ticket: int) -> bool:
         return _check(load_library().fc_save_pack_done(self.handle, ticket),
                       "fc_save_pack_done") == FC_OK
+
+    def save_cancel(self, ticket: int) -> bool:
+        """Drop a held save before any byte of the segment changed; False when the
+        drain had already been released."""
+        rc = load_library().fc_save_cancel(self.handle, ticket)
+        if rc == FC_EBUSY:
+            return False
+        _check(rc, "fc_save_cancel")
+        return True
 
     def save_sources_wait(self, ticket: int):
         """Block until save `ticket` no longer reads the source tensors."""

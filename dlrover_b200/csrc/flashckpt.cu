@@ -967,6 +967,25 @@ extern "C" int fc_save_release(fc_ctx* c, uint64_t ticket) {
   return FC_OK;
 }
 
+extern "C" int fc_save_cancel(fc_ctx* c, uint64_t ticket) {
+  if (!c) return fail(FC_EINVAL, "fc_save_cancel: null ctx%s%s");
+  {
+    std::lock_guard<std::mutex> lk(c->mu);
+    if (c->held_ticket != ticket || ticket == 0)
+      return fail(FC_EBUSY, "fc_save_cancel: the drain is not held (any more)%s%s");
+    for (auto it = c->jobs.begin(); it != c->jobs.end(); ++it)
+      if (it->ticket == ticket) {
+        c->jobs.erase(it);
+        break;
+      }
+    c->held_ticket = 0;
+    c->drained_ticket = std::max(c->drained_ticket, ticket);  // nothing will be written
+    if (c->direct_ticket == ticket) c->inplace_done_ticket = ticket;
+  }
+  c->cv.notify_all();
+  return FC_OK;
+}
+
 static int save_async_impl(fc_plan* p, void* host_base, void* compute_stream, uint64_t* ticket,
                            bool hold) {
   if (!p || (!host_base && p->payload)) return fail(FC_EINVAL, "fc_save_async: null argument%s%s");

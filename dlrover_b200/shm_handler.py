@@ -332,8 +332,14 @@ class PendingSave:
                 if self._pre_drain is not None:
                     try:
                         self._pre_drain()  # e.g. publish writing_shm=True to the agent
-                    finally:
-                        self._ctx.save_release(self._ticket)
+                    except BaseException:
+                        # the agent does not know the segment is about to change: leave
+                        # every byte of it alone (the previous checkpoint stays valid)
+                        if not self._ctx.save_cancel(self._ticket):
+                            self._ctx.save_release(self._ticket)
+                            self._ctx.save_wait(self._ticket)
+                        raise
+                    self._ctx.save_release(self._ticket)
                 if self._ctx is not None:
                     self._ctx.save_wait(self._ticket)
                     self.timings = self._ctx.save_timings(self._ticket)

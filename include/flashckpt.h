@@ -158,6 +158,10 @@ int fc_save_async(fc_plan* plan, void* host_base, void* compute_stream,
  * (In the bounded-arena mode the save is complete on return; release is a no-op.) */
 int fc_save_async_held(fc_plan* plan, void* host_base, void* compute_stream, uint64_t* ticket);
 int fc_save_release(fc_ctx* ctx, uint64_t ticket);
+/* Drop a held save instead of releasing it (the peer could not be told that the
+ * segment is about to change): no byte of the segment is touched, the ticket counts
+ * as complete.  FC_EBUSY if the drain is not held any more. */
+int fc_save_cancel(fc_ctx* ctx, uint64_t ticket);
 /* In-place save, no snapshot and no arena: the drain DMAs every span straight
  * from the source tensors into host_base+offset (paced like fc_save_async; small
  * spans share a batch).  Nothing runs on `compute_stream` — the drain is only

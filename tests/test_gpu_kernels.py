@@ -357,3 +357,31 @@ def test_hybrid_save_snapshot_tail_in_place_head(cuda_device):
     with pytest.raises(native.NativeError):
         plan.save_hybrid_async(host.data_ptr(), offsets[2] + 1, stream)
     plan.destroy()
+
+
+def test_held_save_can_be_cancelled(cuda_device):
+    """fc_save_cancel: a held save is dropped before a byte of the segment changed;
+    once released it cannot be cancelled any more."""
+    ctx = native.get_context(0)
+    t = torch.arange(1 << 20, dtype=torch.int32).cuda()
+    n = t.numel() * 4
+    ctx.arena_reserve(n)
+    plan = ctx.plan([t.data_ptr()], [0], [n])
+    host = torch.full((n,), 7, dtype=torch.uint8).pin_memory()
+    stream = torch.cuda.current_stream()
+    for direct in (False, True):
+        if direct:
+            ticket = plan.save_direct_async(host.data_ptr(), stream, hold=True)
+        else:
+            ticket = plan.save_async(host.data_ptr(), stream, hold=True)
+        assert not ctx.save_poll(ticket)
+        assert ctx.save_cancel(ticket)
+        ctx.save_wait(ticket)                 # returns: the ticket counts as complete
+        assert ctx.save_pack_done(ticket)
+        torch.cuda.synchronize()
+        assert (host.numpy() == 7).all()      # untouched
+    ticket = plan.save_async(host.data_ptr(), stream)   # the context is usable again
+    assert not ctx.save_cancel(ticket)        # not held: too late
+    ctx.save_wait(ticket)
+    assert np.array_equal(host.numpy().view(np.int32), np.arange(1 << 20, dtype=np.int32))
+    plan.destroy()
