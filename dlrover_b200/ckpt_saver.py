@@ -668,8 +668,8 @@ class TempDirCheckpointSaver(AsyncCheckpointSaver):
     def _get_tmp_ckpt_dir(self, step: int):
         return os.path.join(self.checkpoint_dir, self._STAGE_DIR, str(step))
 
-    def commit_checkpoint(self, step: int, step_done_dir: str, tmp_path: str = "",  # type: ignore
-                          target_path: str = "", timeout=600):
+    def commit_checkpoint(self, step: int, step_done_dir: str, tmp_path: str,  # type: ignore
+                          target_path: str, timeout=600):
         logger.info(f"Start commit checkpoint tmp_path: {tmp_path}, path: {target_path}")
         start = time.time()
         success = False
