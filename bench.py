@@ -400,6 +400,15 @@ def run_ours(args):
 
     if world > 1:
         dist.barrier()
+    # the saver daemon unlinks the segments when this process ends; do not rely on it
+    # alone — the driver runs several bench processes back to back on one box and
+    # 16 GB per rank of leaked tmpfs would add up
+    shm = ckpt.engine._shm_handler.shared_memory
+    if shm is not None:
+        try:
+            shm.unlink()
+        except (FileNotFoundError, OSError):
+            pass
     ckpt.engine.close()
     if rank == 0:
         line = {
