@@ -58,6 +58,14 @@ def run_env(monkeypatch, tmp_path):
             pass
         AsyncCheckpointSaver._saver_instance = None
     shutil.rmtree(os.path.join("/tmp/ckpt_sock", run_id), ignore_errors=True)
+    # whatever a failed test left behind (segments are up to 16 GB on the GPU box)
+    import glob
+
+    for leftover in glob.glob(f"/dev/shm/{run_id}_*"):
+        try:
+            os.unlink(leftover)
+        except OSError:
+            pass
     import glob
 
     for f in glob.glob(f"/dev/shm/{run_id}_*"):
