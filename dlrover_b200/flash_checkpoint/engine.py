@@ -170,6 +170,13 @@ def start_async_save():
                 saver.close()
             except Exception:
                 pass
+        if os.getenv("TORCHELASTIC_RUN_ID", ""):
+            # this run's socket namespace was ours alone
+            import shutil
+
+            from ..common.multi_process import _socket_root
+
+            shutil.rmtree(_socket_root(), ignore_errors=True)
         os._exit(0)
 
     signal.signal(signal.SIGTERM, shutdown)
