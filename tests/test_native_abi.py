@@ -65,3 +65,47 @@ def test_missing_gpu_is_loud():
         pytest.skip("has a GPU")
     with pytest.raises(native.NativeError):
         native.Context(0)
+
+
+def _header_prototypes():
+    text = open(os.path.join(ROOT, "include", "flashckpt.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    text = re.sub(r"//[^\n]*", "", text)
+    protos = {}
+    for ret, name, args in re.findall(r"([A-Za-z_][\w\s\*]*?)\b(fc_[a-z_0-9]+)\s*\(([^;{]*?)\)\s*;",
+                                      text, flags=re.S):
+        args = " ".join(args.split())
+        params = [] if args in ("", "void") else [a.strip() for a in args.split(",")]
+        protos[name] = (" ".join(ret.split()), params)
+    return protos
+
+
+def _c_kind(decl: str) -> str:
+    if "*" in decl:
+        return "ptr"
+    for c, kind in (("uint64_t", "u64"), ("uint32_t", "u32"), ("int", "int"), ("float", "float")):
+        if re.search(rf"\b{c}\b", decl):
+            return kind
+    return "?"
+
+
+def _ctypes_kind(t) -> str:
+    if t is None:
+        return "void"
+    if t is ctypes.c_void_p or t is ctypes.c_char_p or isinstance(t, type(ctypes.POINTER(ctypes.c_int))):
+        return "ptr"
+    return {ctypes.c_uint64: "u64", ctypes.c_uint32: "u32", ctypes.c_int: "int",
+            ctypes.c_float: "float"}.get(t, "?")
+
+
+def test_ctypes_signatures_agree_with_the_header():
+    """Every prototype of include/flashckpt.h against the ctypes declaration that
+    calls it: argument count and kind (pointer / u64 / u32 / int), return kind."""
+    protos = _header_prototypes()
+    assert sorted(protos) == sorted(native._SIGNATURES)
+    for name, (ret, params) in protos.items():
+        restype, argtypes = native._SIGNATURES[name]
+        assert len(argtypes) == len(params), f"{name}: {len(argtypes)} ctypes args, header has {params}"
+        for i, (decl, t) in enumerate(zip(params, argtypes)):
+            assert _c_kind(decl) == _ctypes_kind(t), f"{name} arg {i}: header '{decl}' vs ctypes {t}"
+        assert _c_kind(ret) == _ctypes_kind(restype), f"{name}: return '{ret}' vs ctypes {restype}"
