@@ -160,7 +160,9 @@ int fc_save_async_held(fc_plan* plan, void* host_base, void* compute_stream, uin
 int fc_save_release(fc_ctx* ctx, uint64_t ticket);
 /* Drop a held save instead of releasing it (the peer could not be told that the
  * segment is about to change): no byte of the segment is touched, the ticket counts
- * as complete.  FC_EBUSY if the drain is not held any more. */
+ * as complete.  FC_EBUSY if the drain is not held any more.  Mirrors the reference
+ * raising "Fail to set metadata!" (multi_process.py:648-649) from save_state_dict
+ * (ckpt_saver.py:315-318) BEFORE its copy loop starts. */
 int fc_save_cancel(fc_ctx* ctx, uint64_t ticket);
 /* In-place save, no snapshot and no arena: the drain DMAs every span straight
  * from the source tensors into host_base+offset (paced like fc_save_async; small
@@ -179,7 +181,8 @@ int fc_save_direct_async(fc_plan* plan, void* host_base, void* compute_stream, i
  * are snapshotted into the arena (which must hold arena_end - cut bytes; its byte 0
  * stands for offset `cut`), the tensors below `cut` are drained in place — first, so
  * that they are released as early as possible.  Spends whatever HBM is to spare on
- * shortening the time the sources stay frozen: (bytes below cut) / PCIe rate. */
+ * shortening the time the sources stay frozen: (bytes below cut) / PCIe rate.
+ * (The reference keeps the sources frozen for the whole copy, ckpt_saver.py:198-231.) */
 int fc_save_hybrid_async(fc_plan* plan, void* host_base, void* compute_stream, uint64_t cut,
                          int hold, uint64_t* ticket);
 /* FC_OK once nothing of save `ticket` reads the source tensors any more (they may
