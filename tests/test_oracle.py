@@ -97,3 +97,35 @@ def test_ref_port_matches_golden(name):
         del got
     finally:
         saver.close()
+
+
+def test_product_never_touches_the_oracle_or_the_reference():
+    """The oracle is the checker, never the thing shipped: nothing under dlrover_b200/
+    imports it, names it, or reads /root/reference at run time (compat.py may NAME the
+    reference's module paths — as strings to alias — but never opens the checkout)."""
+    import ast
+    import os
+
+    root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "dlrover_b200")
+    offenders = []
+    for dirpath, _, files in os.walk(root):
+        for f in files:
+            path = os.path.join(dirpath, f)
+            if f.endswith((".cu", ".cuh", ".h")):
+                if "oracle" in open(path).read():
+                    offenders.append(path)
+                continue
+            if not f.endswith(".py"):
+                continue
+            src = open(path).read()
+            if "/root/reference" in src:
+                offenders.append(path + " (reads the reference checkout)")
+            for node in ast.walk(ast.parse(src)):
+                names = []
+                if isinstance(node, ast.Import):
+                    names = [a.name for a in node.names]
+                elif isinstance(node, ast.ImportFrom):
+                    names = [node.module or ""]
+                if any(n == "oracle" or n.startswith("oracle.") for n in names):
+                    offenders.append(path)
+    assert not offenders, offenders
