@@ -403,6 +403,7 @@ class SharedMemoryHandler:
         self.last_save_in_place = False
         self.last_restore_stats: Dict[str, float] = {}
         self.last_hybrid_cut = None
+        self._snapshot_ceiling = 0  # largest snapshot arena HBM turned out to have room for
         self._last_ticket = None
         if not host:
             # a drain still in flight when the interpreter exits must finish (the
@@ -598,6 +599,8 @@ class SharedMemoryHandler:
                          daemon=True).start()
         return pending
 
+    MIN_SNAPSHOT_BYTES = 64 << 20  # below this a snapshot part is not worth a kernel
+
     def _hybrid_cut(self, stager: _DeviceStager, plan, device_ranges) -> Optional[int]:
         """In-place save with a snapshot budget: the segment offset from which the
         tensors fit into the arena (None: no budget / no arena -> pure in-place)."""
@@ -605,12 +608,19 @@ class SharedMemoryHandler:
         if budget <= 0:
             return None
         want = min(budget, plan.arena_end)
-        try:
-            if stager.ctx.arena_info()[1] < want:
+        if self._snapshot_ceiling:
+            want = min(want, self._snapshot_ceiling)
+        while stager.ctx.arena_info()[1] < want:
+            try:
                 stager.ctx.arena_reserve(want)
-        except native.NativeError as e:
-            if e.code != native.FC_ENOMEM:
-                raise
+            except native.NativeError as e:
+                if e.code != native.FC_ENOMEM:
+                    raise
+                # no room for that much: remember it, try half (a failed grow has
+                # released the previous arena to make room)
+                self._snapshot_ceiling = want = want // 2
+                if want < self.MIN_SNAPSHOT_BYTES:
+                    break
         cap = min(stager.ctx.arena_info()[1], budget)
         end, cut = plan.arena_end, None
         for _, off, _ in sorted(device_ranges, key=lambda r: r[1], reverse=True):
