@@ -23,6 +23,7 @@ FILES = {
     FC + "megatron_engine.py": "dlrover_b200.flash_checkpoint.engine",
     FC + "fsdp_engine.py": "dlrover_b200.flash_checkpoint.fsdp_engine",
     FC + "replica.py": "dlrover_b200.flash_checkpoint.replica",
+    FC + "hf_trainer.py": "dlrover_b200.flash_checkpoint.hf_trainer",
     "dlrover/python/elastic_agent/torch/ckpt_saver.py": "dlrover_b200.ckpt_saver",
     "dlrover/python/common/storage.py": "dlrover_b200.common.storage",
     "dlrover/python/common/multi_process.py": "dlrover_b200.common.multi_process",

@@ -92,3 +92,20 @@ def test_signature_matches_reference(rel, module, name, params):
     for p in named[len(want):]:
         assert p.default is not inspect.Parameter.empty, \
             f"{key}: extra argument {p.name} must have a default"
+
+
+def test_module_layout_mirrors_the_reference():
+    """Every module of the reference's flash_checkpoint package has a same-named module
+    here that exposes the same public classes and functions (so that switching is a
+    change of the package prefix only)."""
+    prefix = "dlrover/trainer/torch/flash_checkpoint/"
+    for rel, entry in GOLDEN.items():
+        if not rel.startswith(prefix):
+            continue
+        name = os.path.basename(rel)[:-3]
+        mod = importlib.import_module(f"dlrover_b200.flash_checkpoint.{name}")
+        for qual in entry["api"]:
+            top = qual.split(".")[0]
+            if f"{os.path.basename(rel)}:{top}" in NOT_CARRIED_OVER:
+                continue
+            assert hasattr(mod, top), f"dlrover_b200.flash_checkpoint.{name} lacks {top}"
