@@ -80,6 +80,10 @@ _SIGNATURES = {
     "fc_save_wait": (ctypes.c_int, [_vp, _u64]),
     "fc_save_timings": (ctypes.c_int, [_vp, _u64, _fp, _fp, _fp]),
     "fc_set_drain": (ctypes.c_int, [_vp, _u64, ctypes.c_int]),
+    "fc_host_unpack": (
+        ctypes.c_int,
+        [_vp, _u32, ctypes.POINTER(_vp), ctypes.POINTER(_u64), ctypes.POINTER(_u64), ctypes.c_int],
+    ),
     "fc_host_pack": (
         ctypes.c_int,
         [_vp, _u32, ctypes.POINTER(_vp), ctypes.POINTER(_u64), ctypes.POINTER(_u64), ctypes.c_int],
@@ -418,6 +422,19 @@ def host_pack(dst_addr: int, ptrs: Sequence[int], offsets: Sequence[int],
     a_len = (_u64 * n)(*[int(b) for b in nbytes])
     _check(load_library().fc_host_pack(dst_addr, n, a_ptr, a_off, a_len, int(threads)),
            "fc_host_pack")
+
+
+def host_unpack(src_addr: int, ptrs: Sequence[int], offsets: Sequence[int],
+                nbytes: Sequence[int], threads: int = 1):
+    """Multi-threaded memcpy out of the segment into host-resident ranges (no GPU)."""
+    n = len(ptrs)
+    if n == 0:
+        return
+    a_ptr = (_vp * n)(*[int(p) for p in ptrs])
+    a_off = (_u64 * n)(*[int(o) for o in offsets])
+    a_len = (_u64 * n)(*[int(b) for b in nbytes])
+    _check(load_library().fc_host_unpack(src_addr, n, a_ptr, a_off, a_len, int(threads)),
+           "fc_host_unpack")
 
 
 _contexts = {}

@@ -1245,12 +1245,13 @@ extern "C" int fc_set_drain(fc_ctx* c, uint64_t piece_bytes, int depth) {
 // straight into the segment with a (multi-threaded) memcpy, no device hop.
 
 struct HostJob {
-  uint8_t* dst;
-  const void* const* src;
+  uint8_t* dst;             // segment base (the "packed" side)
+  const void* const* src;   // the ranges (the "tensor" side)
   const uint64_t* off;
   const uint64_t* nbytes;
   uint64_t first, last;
   uint64_t skip_first, trim_last;  // byte sub-range of the first / last range
+  bool unpack;              // false: ranges -> segment, true: segment -> ranges
 };
 
 static void* host_pack_worker(void* arg) {
@@ -1258,19 +1259,37 @@ static void* host_pack_worker(void* arg) {
   for (uint64_t i = j->first; i < j->last; ++i) {
     uint64_t lo = (i == j->first) ? j->skip_first : 0;
     uint64_t hi = (i + 1 == j->last) ? j->trim_last : j->nbytes[i];
-    if (hi > lo)
-      memcpy(j->dst + j->off[i] + lo, static_cast<const uint8_t*>(j->src[i]) + lo, hi - lo);
+    if (hi <= lo) continue;
+    uint8_t* packed = j->dst + j->off[i] + lo;
+    uint8_t* range = static_cast<uint8_t*>(const_cast<void*>(j->src[i])) + lo;
+    if (j->unpack)
+      memcpy(range, packed, hi - lo);
+    else
+      memcpy(packed, range, hi - lo);
   }
   return nullptr;
 }
 
+static int host_copy(void* base, uint32_t n, const void* const* ranges, const uint64_t* off,
+                     const uint64_t* nbytes, int threads, bool unpack, const char* who);
+
 extern "C" int fc_host_pack(void* dst_base, uint32_t n, const void* const* src,
                             const uint64_t* off, const uint64_t* nbytes, int threads) {
-  if (!dst_base || (n && (!src || !off || !nbytes)))
-    return fail(FC_EINVAL, "fc_host_pack: null argument%s%s");
+  return host_copy(dst_base, n, src, off, nbytes, threads, false, "fc_host_pack");
+}
+
+extern "C" int fc_host_unpack(const void* src_base, uint32_t n, void* const* dst,
+                              const uint64_t* off, const uint64_t* nbytes, int threads) {
+  return host_copy(const_cast<void*>(src_base), n, dst, off, nbytes, threads, true,
+                   "fc_host_unpack");
+}
+
+static int host_copy(void* dst_base, uint32_t n, const void* const* src, const uint64_t* off,
+                     const uint64_t* nbytes, int threads, bool unpack, const char* who) {
+  if (!dst_base || (n && (!src || !off || !nbytes))) return fail(FC_EINVAL, "%s: null argument%s", who);
   uint64_t total = 0;
   for (uint32_t i = 0; i < n; ++i) {
-    if (nbytes[i] && !src[i]) return fail(FC_EINVAL, "fc_host_pack: null source%s%s");
+    if (nbytes[i] && !src[i]) return fail(FC_EINVAL, "%s: null range%s", who);
     total += nbytes[i];
   }
   if (total == 0) return FC_OK;
@@ -1282,7 +1301,7 @@ extern "C" int fc_host_pack(void* dst_base, uint32_t n, const void* const* src,
   uint32_t i = 0;
   uint64_t inner = 0;  // bytes of range i already assigned
   while (i < n) {
-    HostJob j{static_cast<uint8_t*>(dst_base), src, off, nbytes, i, i, inner, 0};
+    HostJob j{static_cast<uint8_t*>(dst_base), src, off, nbytes, i, i, inner, 0, unpack};
     uint64_t need = share;
     while (i < n && need > 0) {
       uint64_t left = nbytes[i] - inner;

@@ -784,9 +784,15 @@ class SharedMemoryHandler:
         walk(target, meta_dict, "")
         stats = {"device_bytes": 0.0, "host_bytes": 0.0, "fill_ms": 0.0, "scatter_ms": 0.0}
         with torch.no_grad():
-            for t, m in host_pairs:
+            strided = [(t, m) for t, m in host_pairs if not t.is_contiguous()]
+            dense = [(t, m) for t, m in host_pairs if t.is_contiguous()]
+            for t, m in strided:  # rare: let torch handle the strides
                 t.copy_(_read_tensor_from_buf(m, self.shared_memory))
-                stats["host_bytes"] += m.numel * m.element_size
+            if dense:
+                native.host_unpack(self.shared_memory.address, [t.data_ptr() for t, _ in dense],
+                                   [m.offset for _, m in dense],
+                                   [m.numel * m.element_size for _, m in dense], _host_threads())
+            stats["host_bytes"] = float(sum(m.numel * m.element_size for _, m in host_pairs))
             if device_pairs:
                 for t, _ in device_pairs:
                     if not t.is_contiguous():

@@ -216,6 +216,12 @@ int fc_set_drain(fc_ctx* ctx, uint64_t piece_bytes, int depth);
  * _write_shared_memory (ckpt_saver.py:221-231). */
 int fc_host_pack(void* dst_base, uint32_t n, const void* const* src, const uint64_t* off,
                  const uint64_t* nbytes, int threads);
+/* The inverse for CPU targets: nbytes[i] bytes at src_base+off[i] are memcpy'd to
+ * dst[i] with the same byte-balanced threading.  Replaces the per-tensor
+ * `param.copy_(view_on_the_segment)` loop a user runs after load_state_dict
+ * (ckpt_saver.py:144-161 hands out the views) in the CPU/gloo configuration. */
+int fc_host_unpack(const void* src_base, uint32_t n, void* const* dst, const uint64_t* off,
+                   const uint64_t* nbytes, int threads);
 
 /* ---- restore: fill + scatter ---------------------------------------------- */
 

@@ -109,3 +109,25 @@ def test_ctypes_signatures_agree_with_the_header():
         for i, (decl, t) in enumerate(zip(params, argtypes)):
             assert _c_kind(decl) == _ctypes_kind(t), f"{name} arg {i}: header '{decl}' vs ctypes {t}"
         assert _c_kind(ret) == _ctypes_kind(restype), f"{name}: return '{ret}' vs ctypes {restype}"
+
+
+def test_host_unpack_is_the_inverse_of_host_pack():
+    rng = np.random.default_rng(5)
+    sizes = (0, 1, 4097, 9 << 20, 33, 5 << 20)
+    srcs = [rng.integers(0, 256, size=s, dtype=np.uint8) for s in sizes]
+    offs, o = [], 3
+    for s in srcs:
+        offs.append(o)
+        o += s.size + 1          # gaps between the ranges
+    seg = np.zeros(o, dtype=np.uint8)
+    native.host_pack(seg.ctypes.data, [s.ctypes.data if s.size else 0 for s in srcs], offs,
+                     [s.size for s in srcs], 4)
+    for threads in (1, 3, 8):
+        outs = [np.zeros(s, dtype=np.uint8) for s in sizes]
+        native.host_unpack(seg.ctypes.data, [t.ctypes.data if t.size else 0 for t in outs], offs,
+                           list(sizes), threads)
+        for a, b in zip(outs, srcs):
+            assert np.array_equal(a, b)
+    lib = native.load_library()
+    assert lib.fc_host_unpack(None, 0, None, None, None, 1) == native.FC_EINVAL
+    assert b"fc_host_unpack" in lib.fc_last_error()

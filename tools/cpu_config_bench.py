@@ -39,6 +39,23 @@ full = {"model_states": sd, DLROVER_CKPT_CONFIG_KEY: CheckpointConfig(step=1, pa
 t = timeit(lambda: h.save_state_dict(full))
 out["ours_ms"] = t * 1e3
 out["ours_GBps"] = S / t / 1e9
+# restore into live CPU tensors: ours (fc_host_unpack, all cores) vs what a user of the
+# reference does (load_state_dict -> views on the segment, then one copy_ per tensor)
+target = {k: torch.empty_like(v) for k, v in sd.items()}
+t = timeit(lambda: h.restore_into({"model_states": target}))
+out["ours_restore_ms"] = t * 1e3
+assert all(torch.equal(target[k], sd[k]) for k in list(sd)[:3] + list(sd)[-2:])
+
+
+def ref_style_restore():
+    views = h.load_state_dict()["model_states"]
+    with torch.no_grad():
+        for k, v in target.items():
+            v.copy_(views[k])
+
+
+t = timeit(ref_style_restore)
+out["reference_style_restore_ms"] = t * 1e3
 h.unlink()
 h.close()
 
