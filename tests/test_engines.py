@@ -377,3 +377,43 @@ def test_guard_optimizer_unwraps_framework_optimizers(agent, tmp_path):
     engine.guard_if_in_place(b)
     assert len(b._optimizer_step_pre_hooks) == 1
     engine.close()
+
+
+@pytest.mark.timeout(180)
+def test_rapid_saves_never_persist_a_torn_checkpoint(agent, tmp_path):
+    """Back-to-back memory saves while the agent persists earlier steps: a save that
+    finds the shard lock taken is skipped (reference semantics), and every file that
+    does reach the disk holds exactly the state of its step."""
+    engine = FullCheckpointEngine(str(tmp_path), PosixDiskStorage())
+    w = torch.zeros(1 << 20)               # 4 MB
+    aux = torch.zeros(3, dtype=torch.int64)
+    disk_steps, skipped = [], 0
+    for step in range(1, 41):
+        w.fill_(float(step))
+        aux.fill_(step)
+        sd = {"w": w, "aux": aux, "step": step}
+        path = str(tmp_path / str(step) / "rank_0.pt")
+        if step % 4 == 0:
+            if engine.save_to_storage(step, {MODEL: sd}, {MODEL: path}):
+                disk_steps.append(step)
+            else:
+                skipped += 1
+        else:
+            if not engine.save_to_memory(step, {MODEL: sd}, {MODEL: path}):
+                skipped += 1
+    engine.wait_latest_checkpoint(timeout=120)
+    time.sleep(0.5)
+    found = sorted(int(d) for d in os.listdir(tmp_path) if d.isdigit())
+    assert found, "nothing was persisted"
+    assert set(found) <= set(disk_steps)
+    for step in found:
+        f = tmp_path / str(step) / "rank_0.pt"
+        if not f.exists():
+            continue                        # a later step's commit may have replaced it
+        back = torch.load(f)
+        assert back["step"] == step
+        assert float(back["w"].min()) == float(back["w"].max()) == float(step)
+        assert back["aux"].tolist() == [step] * 3
+    tracker = int((tmp_path / "dlrover_latest.txt").read_text())
+    assert tracker == max(found)
+    engine.close()
