@@ -401,7 +401,10 @@ def test_rapid_saves_never_persist_a_torn_checkpoint(agent, tmp_path):
         else:
             if not engine.save_to_memory(step, {MODEL: sd}, {MODEL: path}):
                 skipped += 1
-    engine.wait_latest_checkpoint(timeout=120)
+    # A DISK save can be dropped by design: if the next memory save wins the race for the
+    # shard lock, the agent finds a newer step in memory than its SAVE event names and
+    # refuses (ckpt_saver.py:698-704 in the reference) — so do not wait long for it.
+    engine.wait_latest_checkpoint(timeout=15)
     time.sleep(0.5)
     found = sorted(int(d) for d in os.listdir(tmp_path) if d.isdigit())
     assert found, "nothing was persisted"
