@@ -133,6 +133,41 @@ def timer(func):
     return wrapper
 
 
+class _EventForwarder:
+    """Delivers checkpoint events to the agent's bounded queue from a daemon thread,
+    in submission order (see CheckpointEngine._notify_save_event)."""
+
+    def __init__(self, shared_queue):
+        import queue
+        import threading
+
+        self._target = shared_queue
+        self._backlog = queue.Queue()
+        self._pending = 0
+        self._lock = threading.Lock()
+        threading.Thread(target=self._run, name="ckpt-event-forwarder", daemon=True).start()
+
+    def idle(self) -> bool:
+        with self._lock:
+            return self._pending == 0
+
+    def submit(self, event):
+        with self._lock:
+            self._pending += 1
+        self._backlog.put(event)
+
+    def _run(self):
+        while True:
+            event = self._backlog.get()
+            try:
+                self._target.put(event)  # blocks while the agent is busy
+            except Exception as e:  # agent gone: nothing to notify
+                logger.warning(f"could not deliver {event}: {e}")
+            finally:
+                with self._lock:
+                    self._pending -= 1
+
+
 def _torch_optimizers(obj, depth=0):
     """The torch.optim.Optimizer objects under a (possibly wrapped) optimizer."""
     if obj is None or depth > 4:
@@ -528,7 +563,23 @@ class CheckpointEngine(metaclass=ABCMeta):
             time.sleep(3)
 
     def _notify_save_event(self, step):
-        self._event_queue.put(CheckpointEvent(type=CheckpointEventType.SAVE, step=step))
+        """Tell the agent to persist `step`.  The event queue holds ONE event
+        (multi_process.py SharedQueue maxsize=1, as in the reference): while the agent
+        still chews on the previous one — its step-consistency wait alone is 15 s
+        (ckpt_saver.py:777) — a blocking put would park the training thread.  Deliver
+        inline when the queue is free, else through a forwarder thread, in order."""
+        event = CheckpointEvent(type=CheckpointEventType.SAVE, step=step)
+        forwarder = self.__dict__.get("_event_forwarder")
+        if forwarder is None or forwarder.idle():
+            try:
+                if self._event_queue.empty():
+                    self._event_queue.put(event)
+                    return
+            except Exception:
+                pass  # fall through: let the forwarder retry
+        if forwarder is None:
+            forwarder = self.__dict__["_event_forwarder"] = _EventForwarder(self._event_queue)
+        forwarder.submit(event)
 
     # -- to be provided by concrete engines ------------------------------------------------
     @abstractmethod

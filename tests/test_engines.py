@@ -396,6 +396,10 @@ def test_rapid_saves_never_persist_a_torn_checkpoint(agent, tmp_path):
         if step % 4 == 0:
             if engine.save_to_storage(step, {MODEL: sd}, {MODEL: path}):
                 disk_steps.append(step)
+                # a real save holds the shard lock for the length of its drain, by
+                # which time the agent is queued on it; these 4 MB CPU saves are over
+                # in 2 ms, so give the agent the same head start
+                time.sleep(0.1)
             else:
                 skipped += 1
         else:
@@ -420,3 +424,33 @@ def test_rapid_saves_never_persist_a_torn_checkpoint(agent, tmp_path):
     tracker = int((tmp_path / "dlrover_latest.txt").read_text())
     assert tracker == max(found)
     engine.close()
+
+
+def test_save_event_never_parks_the_training_thread(run_env):
+    """The agent's event queue holds one event; while the agent has not taken it, the
+    next notification goes through the forwarder thread instead of blocking the caller,
+    and events still arrive in order."""
+    from dlrover_b200.flash_checkpoint.engine import CheckpointEngine
+
+    owner = SharedQueue("events", create=True)            # the agent's side, maxsize=1
+    client = SharedQueue("events", create=False)
+
+    class Probe:                                           # just enough of an engine
+        _event_queue = client
+
+    probe = Probe()
+    t0 = time.time()
+    for step in (10, 20, 30):
+        CheckpointEngine._notify_save_event(probe, step)
+    assert time.time() - t0 < 1.0                          # a blocking put would hang here
+    got = [owner.get(timeout=10).step for _ in range(3)]
+    assert got == [10, 20, 30]
+    deadline = time.time() + 5
+    while not probe.__dict__["_event_forwarder"].idle() and time.time() < deadline:
+        time.sleep(0.05)
+    assert probe.__dict__["_event_forwarder"].idle()
+    CheckpointEngine._notify_save_event(probe, 40)         # idle again: delivered inline
+    assert owner.get(timeout=5).step == 40
+    client.close()
+    owner.close()
+    owner.unlink()
