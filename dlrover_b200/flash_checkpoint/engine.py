@@ -426,7 +426,9 @@ class CheckpointEngine(metaclass=ABCMeta):
         (Megatron's optimizers, DeepSpeed's ZeRO optimizers) are unwrapped down to the
         torch optimizers whose step() does the writing.  Idempotent; returns the list of
         new hook handles."""
-        guarded = self.__dict__.setdefault("_guarded_optimizers", set())
+        guarded = getattr(self, "_guarded_optimizers", None)
+        if guarded is None:
+            guarded = self._guarded_optimizers = set()
         handles = []
         for opt in _torch_optimizers(optimizer):
             if id(opt) in guarded:
@@ -569,7 +571,7 @@ class CheckpointEngine(metaclass=ABCMeta):
         (ckpt_saver.py:777) — a blocking put would park the training thread.  Deliver
         inline when the queue is free, else through a forwarder thread, in order."""
         event = CheckpointEvent(type=CheckpointEventType.SAVE, step=step)
-        forwarder = self.__dict__.get("_event_forwarder")
+        forwarder = getattr(self, "_event_forwarder", None)
         if forwarder is None or forwarder.idle():
             try:
                 if self._event_queue.empty():
@@ -578,7 +580,7 @@ class CheckpointEngine(metaclass=ABCMeta):
             except Exception:
                 pass  # fall through: let the forwarder retry
         if forwarder is None:
-            forwarder = self.__dict__["_event_forwarder"] = _EventForwarder(self._event_queue)
+            forwarder = self._event_forwarder = _EventForwarder(self._event_queue)
         forwarder.submit(event)
 
     # -- to be provided by concrete engines ------------------------------------------------

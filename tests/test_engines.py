@@ -446,9 +446,9 @@ def test_save_event_never_parks_the_training_thread(run_env):
     got = [owner.get(timeout=10).step for _ in range(3)]
     assert got == [10, 20, 30]
     deadline = time.time() + 5
-    while not probe.__dict__["_event_forwarder"].idle() and time.time() < deadline:
+    while not probe._event_forwarder.idle() and time.time() < deadline:
         time.sleep(0.05)
-    assert probe.__dict__["_event_forwarder"].idle()
+    assert probe._event_forwarder.idle()
     CheckpointEngine._notify_save_event(probe, 40)         # idle again: delivered inline
     assert owner.get(timeout=5).step == 40
     client.close()
