@@ -414,7 +414,10 @@ class SharedMemoryHandler:
 
     # -- lifecycle ------------------------------------------------------------------
     def close(self):
-        self.wait_pending()
+        try:
+            self.wait_pending()
+        except BaseException as e:  # already logged by the completion thread
+            logger.warning(f"closing after a failed drain: {e}")
         if self._stager is not None:
             self._stager.close()
             self._stager = None
