@@ -166,15 +166,19 @@ def ncu_traffic():
 
 
 def run_reference(args):
-    """Times the reference's algorithm (oracle/ref_port.py) on this box."""
+    """Times the reference's algorithm (oracle/ref_port.py) on this box: EVERY rank
+    runs it on its own GPU and its own shard at the same time (as the reference does:
+    one blocking per-tensor copy loop per saving rank), the job's aggregate is
+    reported from the slowest rank's clock."""
     rank, local, world = dist_env()
-    if rank != 0:
-        return 0
     import torch
+    import torch.distributed as dist
 
     from dlrover_b200 import shapes
     from oracle.ref_port import RefPortSaver
 
+    if world > 1:
+        dist.init_process_group("nccl")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     sd = {"model_states": shapes.build_state_dict(
@@ -185,51 +189,60 @@ def run_reference(args):
     try:
         for _ in range(max(args.warmup, 1)):
             saver.save(sd)
-        torch.cuda.synchronize()
+        barrier_sync(world)
         clocks.start()
         t0 = time.perf_counter()
         for _ in range(args.steps):
             saver.save(sd)
         torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
+        dt_mine = time.perf_counter() - t0
+        barrier_sync(world)
+        dt = max_over_ranks(dt_mine, world, dev)
         # restore the reference's way: CPU views on the (pageable) segment, one
         # H2D copy_ per tensor (ckpt_saver.py:144-161 + model.load_state_dict)
         views = shm_layout_read(saver)
-        torch.cuda.synchronize()
+        barrier_sync(world)
         r0 = time.perf_counter()
         with torch.no_grad():
             for k, t in sd["model_states"].items():
                 t.copy_(views["model_states"][k])
         torch.cuda.synchronize()
-        restore_s = time.perf_counter() - r0
+        restore_s = max_over_ranks(time.perf_counter() - r0, world, dev)
         del views
     finally:
         clk = clocks.stop()
         saver.close()
-    gbs = S * args.steps / dt / 1e9
-    line = {
-        "impl": "reference", "metric": METRIC, "value": gbs, "unit": UNIT, "n_gpus": world,
-        "ranks_run": 1,
-        "note": "CPU-side reference path timed on rank 0 only (one shard, one host thread, as the "
-                "reference runs it per rank); with N ranks the reference saves N such shards "
-                "independently, so its N-rank aggregate is at most N x this value",
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
-        "data": "synthetic",
-        "config": workload_config(S, world, args.scale),
-        "stall_ms": {"blocking": dt / args.steps * 1e3,
-                     "note": "the reference blocks the training thread for the whole copy"},
-        "restore": {"reference_ms": restore_s * 1e3, "reference_GBps": S / restore_s / 1e9,
-                    "how": "frombuffer views on the pageable segment + per-tensor copy_ to cuda"},
-        "cpu_baseline": {"value": gbs, "unit": UNIT, "cores": 1, "kind": "port",
-                         "host_cores": os.cpu_count(),
-                         "sample": f"{args.steps} full saves of the {S / 1e9:.2f} GB state_dict: "
-                                   "per-tensor blocking copy_ into a pageable /dev/shm segment "
-                                   "(oracle/ref_port.py restating ckpt_saver.py:198-231)"},
-        "e2e": {"value": gbs, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0, "clocks": clk,
-    }
-    print(json.dumps(line), flush=True)
+    gbs = S * world * args.steps / dt / 1e9
+    if rank == 0:
+        line = {
+            "impl": "reference", "metric": METRIC, "value": gbs, "unit": UNIT, "n_gpus": world,
+            "ranks_run": world,
+            "note": "the reference's memory-save path (oracle/ref_port.py) run on ALL ranks at "
+                    "once, each on its own GPU and shard; value = bytes of all ranks / slowest "
+                    "rank's wall time",
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
+            "data": "synthetic",
+            "config": workload_config(S, world, args.scale),
+            "stall_ms": {"blocking": dt / args.steps * 1e3,
+                         "note": "the reference blocks the training thread for the whole copy"},
+            "restore": {"reference_ms": restore_s * 1e3,
+                        "reference_GBps": S * world / restore_s / 1e9,
+                        "how": "frombuffer views on the pageable segment + per-tensor copy_ to "
+                               "cuda, all ranks at once"},
+            "cpu_baseline": {"value": gbs, "unit": UNIT, "cores": world, "kind": "port",
+                             "host_cores": os.cpu_count(),
+                             "sample": f"{args.steps} full saves of the {S / 1e9:.2f} GB state_dict "
+                                       f"on each of {world} rank(s): per-tensor blocking copy_ into "
+                                       "a pageable /dev/shm segment, one host thread per rank "
+                                       "(oracle/ref_port.py restating ckpt_saver.py:198-231)"},
+            "e2e": {"value": gbs, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0, "clocks": clk,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
     return 0
 
 
@@ -269,9 +282,8 @@ def run_ours(args):
     rank, local, world = dist_env()
     os.environ.setdefault("TORCHELASTIC_RUN_ID", f"fcbench{os.getppid()}")
     os.environ.setdefault("DLROVER_LOG_LEVEL", "WARNING")
-    # NCCL prints "NCCL version ..." to STDOUT at NCCL_DEBUG>=VERSION; stdout is
-    # reserved for the one JSON line
-    os.environ["NCCL_DEBUG"] = os.getenv("BENCH_NCCL_DEBUG", "NONE")
+    # NCCL_DEBUG is left as the launcher set it (its log lines share stdout with the one
+    # JSON line; rank 0 prints that line between two barriers, when NCCL is quiet)
     import torch
     import torch.distributed as dist
 

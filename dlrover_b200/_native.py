@@ -28,6 +28,9 @@ VARIANT_AUTO = 0
 VARIANT_LSU = 1
 VARIANT_TMA = 2
 
+DRAIN_HOST_PACED = 0
+DRAIN_PINGPONG = 1
+
 # every symbol include/flashckpt.h declares: (name, restype, argtypes)
 _u64 = ctypes.c_uint64
 _u32 = ctypes.c_uint32
@@ -44,6 +47,13 @@ _SIGNATURES = {
     "fc_arena_info": (ctypes.c_int, [_vp, ctypes.POINTER(_vp), ctypes.POINTER(_u64)]),
     "fc_host_register": (ctypes.c_int, [_vp, _vp, _u64, ctypes.c_int]),
     "fc_host_unregister": (ctypes.c_int, [_vp, _vp]),
+    "fc_host_register_background": (ctypes.c_int, [_vp, _vp, _u64, _u64]),
+    "fc_host_ready": (ctypes.c_int, [_vp, _vp]),
+    "fc_host_bind_numa": (ctypes.c_int, [_vp, _vp, _u64, ctypes.c_int]),
+    "fc_device_numa_node": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(ctypes.c_int),
+                                           ctypes.POINTER(ctypes.c_int)]),
+    "fc_set_stage": (ctypes.c_int, [_vp, ctypes.c_int, _u64]),
+    "fc_set_drain_mode": (ctypes.c_int, [_vp, ctypes.c_int]),
     "fc_plan_create": (
         ctypes.c_int,
         [_vp, _u32, ctypes.POINTER(_vp), ctypes.POINTER(_u64), ctypes.POINTER(_u64), _u32,
@@ -300,6 +310,35 @@ class Context:
         )
         self._registered[host_ptr] = nbytes
 
+    def host_register_background(self, host_ptr: int, nbytes: int, slice_bytes: int = 0):
+        """Pin the range slice by slice on a library thread; returns at once."""
+        _check(load_library().fc_host_register_background(self.handle, host_ptr, int(nbytes),
+                                                          int(slice_bytes)),
+               "fc_host_register_background")
+        self._registered[host_ptr] = nbytes
+
+    def host_ready(self, host_ptr: int) -> bool:
+        """True once the range is completely pinned (plain DMA); False while a
+        background registration is in progress or the range is unknown."""
+        if host_ptr not in self._registered:
+            return False
+        rc = load_library().fc_host_ready(self.handle, host_ptr)
+        if rc == FC_ENOTREADY:
+            return False
+        _check(rc, "fc_host_ready")
+        return True
+
+    def host_bind_numa(self, host_ptr: int, nbytes: int, remote_per256: int = 0):
+        _check(load_library().fc_host_bind_numa(self.handle, host_ptr, int(nbytes),
+                                                int(remote_per256)), "fc_host_bind_numa")
+
+    def set_stage(self, threads: int = 0, slot_bytes: int = 0):
+        _check(load_library().fc_set_stage(self.handle, int(threads), int(slot_bytes)),
+               "fc_set_stage")
+
+    def set_drain_mode(self, mode: int):
+        _check(load_library().fc_set_drain_mode(self.handle, int(mode)), "fc_set_drain_mode")
+
     def host_unregister(self, host_ptr: int):
         if host_ptr in self._registered:
             _check(load_library().fc_host_unregister(self.handle, host_ptr),
@@ -411,6 +450,14 @@ class Context:
             pass
 
 
+def device_numa_node(device: int) -> Tuple[int, int]:
+    """(NUMA node of the CUDA device or -1, number of NUMA nodes of the host)."""
+    node, n = ctypes.c_int(-1), ctypes.c_int(0)
+    _check(load_library().fc_device_numa_node(int(device), ctypes.byref(node), ctypes.byref(n)),
+           "fc_device_numa_node")
+    return node.value, n.value
+
+
 def host_pack(dst_addr: int, ptrs: Sequence[int], offsets: Sequence[int],
               nbytes: Sequence[int], threads: int = 1):
     """Multi-threaded memcpy of host-resident ranges into the segment (no GPU)."""
@@ -454,5 +501,14 @@ def get_context(device: int) -> Context:
             depth = int(os.getenv("DLROVER_B200_DRAIN_DEPTH", "0") or 0)
             if piece or depth:  # tuning runs only
                 ctx.set_drain(piece << 20, depth)
+            mode = os.getenv("DLROVER_B200_DRAIN_MODE", "")
+            if mode in ("0", "1"):
+                ctx.set_drain_mode(int(mode))
+            threads = int(os.getenv("DLROVER_B200_STAGE_THREADS", "0") or 0)
+            if not threads:
+                # first save / restart restore only; leave cores to the other local ranks
+                local_world = int(os.getenv("LOCAL_WORLD_SIZE", "1") or 1)
+                threads = max(2, min(16, (os.cpu_count() or 2) // max(1, 2 * local_world)))
+            ctx.set_stage(threads, 0)
             _contexts[device] = ctx
         return ctx

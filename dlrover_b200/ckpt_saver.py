@@ -324,10 +324,10 @@ class AsyncCheckpointSaver(metaclass=ABCMeta):
         lock = self._shm_locks[local_shard_id]
         held = False
         try:
-            if handler.shared_memory is None:
-                handler.init_shared_memory(create=False)
             # blocks while the trainer is still filling/draining this shard
             held = bool(lock.acquire())
+            # only now: the trainer may have re-created the segment (size change)
+            handler.refresh_mapping()
             config = handler.get_checkpoint_config(CheckpointConfig())
             if config.step != step:
                 logger.error(f"The step {step} in event is no equal to step {config.step} "
@@ -398,7 +398,9 @@ class AsyncCheckpointSaver(metaclass=ABCMeta):
                 s = handler.get_checkpoint_config(CheckpointConfig()).step
                 if s > 0:
                     steps.append(s)
-            if all(s == step for s in steps):
+            # (at least one shard must hold the step: right after the first save of a
+            # run the agent can be ahead of the trainer's deferred meta publication)
+            if steps and all(s == step for s in steps):
                 return True
             time.sleep(1)
             if time.time() > deadline:
@@ -766,6 +768,7 @@ class FsdpDcpSaver(CommonDirCheckpointSaver):
         else:
             while not self.storage.exists(checkpoint_dir):
                 time.sleep(1)
+        handler.refresh_mapping()
         assert handler.shared_memory is not None
         self.storage.write(handler.shared_memory.buf, path)
         if leader:

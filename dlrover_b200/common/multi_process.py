@@ -340,26 +340,31 @@ class SharedLock(LocalSocketComm):
     def __init__(self, name: str = "", create: bool = False, owner: str = ""):
         self._lock = threading.Lock() if create else None
         self._id = owner
+        # bumps every time the lock is freed: a connection's hold is only valid for
+        # the epoch it was taken in, so a forced release on the owner side
+        # (AsyncCheckpointSaver.release_locks) invalidates it
+        self._epoch = 0
         super().__init__(name, create)
 
     def _dispatch(self, request, held):
         if request.method == "acquire":
             got = self.acquire(**request.args)
             held["lock"] = bool(got)
+            held["epoch"] = self._epoch
             return LockAcquireResponse(acquired=bool(got))
         if request.method == "locked":
             return LockedResponse(locked=self.locked())
         if request.method == "release":
             # only the connection that holds the lock may free it: a stray
             # second release must not drop a lock someone else has since taken
-            if held["lock"]:
+            if held["lock"] and held.get("epoch") == self._epoch:
                 self.release()
-                held["lock"] = False
+            held["lock"] = False
             return SocketResponse()
         raise ValueError(f"unknown lock method {request.method!r}")
 
     def _on_disconnect(self, held):
-        if held.get("lock"):
+        if held.get("lock") and held.get("epoch") == self._epoch:
             logger.info(f"SharedLock({self._name}): holder disconnected, releasing.")
             self.release()
 
@@ -378,6 +383,7 @@ class SharedLock(LocalSocketComm):
             if self._lock.locked():
                 try:
                     self._lock.release()
+                    self._epoch += 1
                 except RuntimeError:
                     pass  # lost a race with another releaser
             return
@@ -573,6 +579,19 @@ class SharedMemory:
     def address(self) -> int:
         """Virtual address of byte 0 (for cudaHostRegister / DMA targets)."""
         return ctypes.addressof(ctypes.c_char.from_buffer(self._mmap))
+
+    def stale(self) -> bool:
+        """True when the NAME no longer refers to the object this mapping came from
+        (the creator unlinked and re-created the segment, e.g. with another size) or
+        the object has been resized: a reader must re-attach."""
+        if self._fd < 0:
+            return True
+        try:
+            mine = os.fstat(self._fd)
+            now = os.stat("/dev/shm" + self._name)
+        except OSError:
+            return True
+        return (mine.st_ino, mine.st_dev) != (now.st_ino, now.st_dev) or now.st_size != self._size
 
     def close(self):
         if self._buf is not None:

@@ -46,8 +46,10 @@
 #include <unistd.h>
 
 #include <algorithm>
+#include <atomic>
 #include <condition_variable>
 #include <deque>
+#include <memory>
 #include <mutex>
 #include <new>
 #include <string>
@@ -94,6 +96,7 @@ struct fc_ctx {
   int device = 0;
   int sm_count = 148;
   cudaStream_t copy_stream = nullptr;
+  cudaStream_t copy_stream2 = nullptr;  // second leg of the ping-pong drain
   uint8_t* arena = nullptr;
   uint64_t arena_bytes = 0;
   uint64_t arena_cap = 0;  // 0 = unlimited; else fc_arena_reserve never allocates more
@@ -115,7 +118,27 @@ struct fc_ctx {
   // restore pipeline state
   cudaEvent_t ev_fill_start = nullptr, ev_fill_end = nullptr, ev_scatter_end = nullptr;
   bool restore_inflight = false;
-  std::vector<void*> registered;
+  // host ranges pinned for DMA: one entry per fc_host_register* call; a background
+  // registration pins slice by slice on its own thread
+  struct HostReg {
+    uint8_t* base = nullptr;
+    uint64_t bytes = 0;
+    uint64_t slice = 0;             // 0: one cudaHostRegister call for the whole range
+    std::vector<void*> done;        // registered slice starts
+    std::thread th;
+    std::atomic<bool> cancel{false};
+    std::atomic<int> state{0};      // 0 in progress, 1 complete, -1 failed
+  };
+  std::vector<std::unique_ptr<HostReg>> regs;
+  // bounce slots of the staged transfers (segment not registered yet)
+  struct StageWorker {
+    cudaStream_t stream = nullptr;
+    uint8_t* slot[2] = {nullptr, nullptr};
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+  };
+  std::vector<StageWorker> stage;
+  uint64_t stage_slot = 8ull << 20;
+  int stage_threads = 8;
   // evidence counters: kernels launched / DMA copies enqueued by this context
   uint64_t n_kernels = 0, n_memcpys = 0;
   // drain pump (one thread per context, started lazily)
@@ -123,6 +146,7 @@ struct fc_ctx {
   std::mutex mu;
   std::condition_variable cv;
   struct DrainJob {
+    int staged_threads = 0;  // > 0: host range not registered, go through the bounce slots
     uint8_t* host = nullptr;
     std::vector<FcRun> runs;
     std::vector<FcSpan> spans;  // in-place save: DMA straight from the tensors
@@ -139,12 +163,120 @@ struct fc_ctx {
   int drain_rc = FC_OK;         // sticky error of the pump
   std::string drain_err;
   cudaEvent_t ring[kDrainRing] = {};
+  cudaEvent_t ring_pp[kDrainRing] = {};  // ping-pong mode: blocking-sync events
+  int drain_mode = FC_DRAIN_HOST_PACED;
   // device/pinned buffers whose cudaFree (a device-wide sync) is deferred to a
   // moment that synchronises anyway
   std::vector<void*> dead_dev, dead_pinned;
   uint64_t drain_piece = kDrainPiece;
   int drain_depth = kDrainDepth;
 };
+
+static fc_ctx::HostReg* reg_covering(fc_ctx* c, const uint8_t* p, uint64_t len);
+
+// ---- staged transfers ---------------------------------------------------------
+// A host range that is not (yet) cudaHostRegister-ed — the segment a restarted
+// trainer has just attached to, or a brand-new one whose registration (3-6 s for
+// 16 GB) has been moved to the background — is moved through pinned bounce slots:
+// T host threads, each with its own stream and two slots, memcpy between the
+// segment and a slot while the DMA of their other slot is in flight.  The
+// reference does the same thing implicitly (a pageable cudaMemcpy is staged by the
+// driver through one small pinned buffer, 11-18 GB/s); this reaches PCIe speed.
+struct StagePiece {
+  uint8_t* dev;
+  uint8_t* host;
+  uint64_t len;
+};
+
+static void stage_pieces(std::vector<StagePiece>& out, uint8_t* dev, uint8_t* host, uint64_t len,
+                         uint64_t slot) {
+  for (uint64_t o = 0; o < len; o += slot)
+    out.push_back({dev + o, host + o, std::min<uint64_t>(slot, len - o)});
+}
+
+static cudaError_t stage_worker_init(fc_ctx* c, fc_ctx::StageWorker& w) {
+  cudaError_t e = cudaSuccess;
+  if (!w.stream) e = cudaStreamCreateWithFlags(&w.stream, cudaStreamNonBlocking);
+  for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
+    if (!w.slot[i]) e = cudaHostAlloc((void**)&w.slot[i], c->stage_slot, cudaHostAllocDefault);
+    if (e == cudaSuccess && !w.ev[i])
+      e = cudaEventCreateWithFlags(&w.ev[i], cudaEventDisableTiming | cudaEventBlockingSync);
+  }
+  return e;
+}
+
+// to_host=false: host -> slot (memcpy) -> device (DMA).  true: the inverse.
+static void stage_worker(fc_ctx* c, int wi, const std::vector<StagePiece>* pieces,
+                         std::atomic<size_t>* next, bool to_host, cudaEvent_t gate,
+                         std::atomic<int>* err) {
+  cudaSetDevice(c->device);
+  fc_ctx::StageWorker& w = c->stage[wi];
+  cudaError_t e = stage_worker_init(c, w);
+  if (e == cudaSuccess && gate) e = cudaStreamWaitEvent(w.stream, gate, 0);
+  const size_t n = pieces->size();
+  if (!to_host) {
+    bool used[2] = {false, false};
+    for (int j = 0; e == cudaSuccess; ++j) {
+      const size_t i = next->fetch_add(1);
+      if (i >= n) break;
+      const StagePiece& pc = (*pieces)[i];
+      const int sl = j & 1;
+      if (used[sl]) e = cudaEventSynchronize(w.ev[sl]);  // the DMA out of this slot is done
+      if (e != cudaSuccess) break;
+      memcpy(w.slot[sl], pc.host, pc.len);
+      e = cudaMemcpyAsync(pc.dev, w.slot[sl], pc.len, cudaMemcpyHostToDevice, w.stream);
+      if (e == cudaSuccess) e = cudaEventRecord(w.ev[sl], w.stream);
+      used[sl] = true;
+    }
+  } else {
+    // software pipeline: the DMA of piece n+1 runs while piece n is copied out
+    size_t cur = next->fetch_add(1);
+    int sl = 0;
+    if (cur < n && e == cudaSuccess) {
+      e = cudaMemcpyAsync(w.slot[0], (*pieces)[cur].dev, (*pieces)[cur].len,
+                          cudaMemcpyDeviceToHost, w.stream);
+      if (e == cudaSuccess) e = cudaEventRecord(w.ev[0], w.stream);
+    }
+    while (cur < n && e == cudaSuccess) {
+      const size_t nxt = next->fetch_add(1);
+      if (nxt < n) {
+        e = cudaMemcpyAsync(w.slot[sl ^ 1], (*pieces)[nxt].dev, (*pieces)[nxt].len,
+                            cudaMemcpyDeviceToHost, w.stream);
+        if (e == cudaSuccess) e = cudaEventRecord(w.ev[sl ^ 1], w.stream);
+      }
+      if (e == cudaSuccess) e = cudaEventSynchronize(w.ev[sl]);
+      if (e != cudaSuccess) break;
+      memcpy((*pieces)[cur].host, w.slot[sl], (*pieces)[cur].len);
+      cur = nxt;
+      sl ^= 1;
+    }
+  }
+  if (w.stream) {
+    cudaError_t e2 = cudaStreamSynchronize(w.stream);
+    if (e == cudaSuccess) e = e2;
+  }
+  if (e != cudaSuccess) {
+    (void)cudaGetLastError();
+    err->store((int)e);
+  }
+}
+
+// Runs the pieces over `threads` workers (the caller is one of them); blocks.
+static cudaError_t stage_run(fc_ctx* c, const std::vector<StagePiece>& pieces, bool to_host,
+                             cudaEvent_t gate, int threads) {
+  if (pieces.empty()) return cudaSuccess;
+  int nt = std::max(1, std::min(threads, 32));
+  nt = (int)std::min<size_t>((size_t)nt, pieces.size());
+  if ((int)c->stage.size() < nt) c->stage.resize(nt);
+  std::atomic<size_t> next{0};
+  std::atomic<int> err{0};
+  std::vector<std::thread> th;
+  for (int i = 1; i < nt; ++i)
+    th.emplace_back(stage_worker, c, i, &pieces, &next, to_host, gate, &err);
+  stage_worker(c, 0, &pieces, &next, to_host, gate, &err);
+  for (auto& t : th) t.join();
+  return (cudaError_t)err.load();
+}
 
 static void pump_main(fc_ctx* c) {
   cudaSetDevice(c->device);
@@ -164,14 +296,56 @@ static void pump_main(fc_ctx* c) {
     if (e == cudaSuccess) e = cudaEventRecord(c->ev_drain_start, c->copy_stream);
     const int depth = std::max(1, std::min(c->drain_depth, kDrainRing));
     uint64_t k = 0, copies = 0;
+    if (job.staged_threads > 0 && e == cudaSuccess) {
+      // host range not registered: bounce through pinned slots (in-place part first)
+      std::vector<StagePiece> pieces;
+      for (const FcSpan& sp : job.spans)
+        stage_pieces(pieces, (uint8_t*)(uintptr_t)sp.tptr, job.host + sp.off, sp.len,
+                     c->stage_slot);
+      if (!pieces.empty()) {
+        e = stage_run(c, pieces, true, c->ev_pack_end, job.staged_threads);
+        copies += pieces.size();
+        pieces.clear();
+      }
+      if (job.direct) {
+        {
+          std::lock_guard<std::mutex> lk(c->mu);
+          c->inplace_done_ticket = job.ticket;
+        }
+        c->cv.notify_all();
+      }
+      for (const FcRun& r : job.runs)
+        stage_pieces(pieces, c->arena + (r.off - job.arena_base), job.host + r.off, r.len,
+                     c->stage_slot);
+      if (e == cudaSuccess) e = stage_run(c, pieces, true, c->ev_pack_end, job.staged_threads);
+      copies += pieces.size();
+      job.runs.clear();
+      job.direct = false;
+    }
+    // a range registered slice by slice: no DMA may straddle two slices
+    uint8_t* reg_base = nullptr;
+    uint64_t reg_slice = 0;
+    if (!job.runs.empty() || !job.spans.empty()) {
+      std::lock_guard<std::mutex> lk(c->mu);
+      const uint64_t first = !job.runs.empty() ? job.runs.front().off : job.spans.front().off;
+      if (fc_ctx::HostReg* r = reg_covering(c, job.host + first, 1)) {
+        reg_base = r->base;
+        reg_slice = r->slice;
+      }
+    }
+    auto clip = [&](const uint8_t* dst, uint64_t len) {
+      if (!reg_slice) return len;
+      const uint64_t in = (uint64_t)(dst - reg_base) % reg_slice;
+      return std::min<uint64_t>(len, reg_slice - in);
+    };
     if (job.direct) {
       // one batch (<= drain_piece bytes, <= 64 copies) in flight, then wait: same
       // pacing rule as below, small tensors share a batch
       uint64_t batch_bytes = 0;
       int batch_n = 0;
       for (const FcSpan& sp : job.spans) {
-        for (uint64_t o = 0; o < sp.len && e == cudaSuccess; o += c->drain_piece) {
-          const uint64_t len = std::min<uint64_t>(c->drain_piece, sp.len - o);
+        for (uint64_t o = 0, len = 0; o < sp.len && e == cudaSuccess; o += len) {
+          len = clip(job.host + sp.off + o, std::min<uint64_t>(c->drain_piece, sp.len - o));
           e = cudaMemcpyAsync(job.host + sp.off + o, (const uint8_t*)(uintptr_t)sp.tptr + o, len,
                               cudaMemcpyDeviceToHost, c->copy_stream);
           ++copies;
@@ -195,17 +369,39 @@ static void pump_main(fc_ctx* c) {
       }
       c->cv.notify_all();
     }
+    const bool pingpong = c->drain_mode == FC_DRAIN_PINGPONG && c->copy_stream2 != nullptr;
+    cudaStream_t last_stream = c->copy_stream;
     for (const FcRun& r : job.runs) {
-      for (uint64_t o = 0; o < r.len && e == cudaSuccess; o += c->drain_piece) {
-        const uint64_t len = std::min<uint64_t>(c->drain_piece, r.len - o);
-        if (k >= (uint64_t)depth) e = cudaEventSynchronize(c->ring[k % depth]);  // piece k-depth
-        if (e == cudaSuccess)
-          e = cudaMemcpyAsync(job.host + r.off + o, c->arena + (r.off - job.arena_base) + o, len,
-                              cudaMemcpyDeviceToHost, c->copy_stream);
-        if (e == cudaSuccess) e = cudaEventRecord(c->ring[k % depth], c->copy_stream);
+      for (uint64_t o = 0, len = 0; o < r.len && e == cudaSuccess; o += len) {
+        uint8_t* dst = job.host + r.off + o;
+        len = clip(dst, std::min<uint64_t>(c->drain_piece, r.len - o));
+        const uint8_t* src = c->arena + (r.off - job.arena_base) + o;
+        if (pingpong) {
+          // Piece k goes to stream k&1 and waits ON THE DEVICE for piece k-1 (the other
+          // stream): neither stream ever has a second copy queued behind the one in
+          // flight, so the copy engine arbitrates between our next piece and a
+          // foreign copy after every piece — and there is no host round trip between
+          // two pieces.  The host only keeps two pieces submitted.
+          cudaStream_t sk = (k & 1) ? c->copy_stream2 : c->copy_stream;
+          if (k >= 2) e = cudaEventSynchronize(c->ring_pp[(k - 2) % kDrainRing]);
+          if (e == cudaSuccess && k >= 1)
+            e = cudaStreamWaitEvent(sk, c->ring_pp[(k - 1) % kDrainRing], 0);
+          if (e == cudaSuccess) e = cudaMemcpyAsync(dst, src, len, cudaMemcpyDeviceToHost, sk);
+          if (e == cudaSuccess) e = cudaEventRecord(c->ring_pp[k % kDrainRing], sk);
+          last_stream = sk;
+        } else {
+          if (k >= (uint64_t)depth) e = cudaEventSynchronize(c->ring[k % depth]);  // piece k-depth
+          if (e == cudaSuccess)
+            e = cudaMemcpyAsync(dst, src, len, cudaMemcpyDeviceToHost, c->copy_stream);
+          if (e == cudaSuccess) e = cudaEventRecord(c->ring[k % depth], c->copy_stream);
+        }
         ++k;
         ++copies;
       }
+    }
+    if (e == cudaSuccess && last_stream != c->copy_stream) {
+      // ev_drain_end is recorded on copy_stream: order it after the last piece
+      e = cudaStreamWaitEvent(c->copy_stream, c->ring_pp[(k - 1) % kDrainRing], 0);
     }
     if (e == cudaSuccess) e = cudaEventRecord(c->ev_drain_end, c->copy_stream);
     if (e == cudaSuccess) e = cudaEventSynchronize(c->ev_drain_end);
@@ -240,7 +436,12 @@ struct fc_plan {
   uint64_t payload = 0, arena_end = 0;
   uint32_t chunk = kDefaultChunk;
   std::vector<FcRun> runs;
-  std::vector<FcItem> h_all;  // host copy of `all`, ascending arena offset (windowed mode)
+  std::vector<FcItem> h_all;  // host copy of `all`, ascending arena offset
+  // bulk/resid/shift are derived from `all` item by item, in the same (ascending
+  // offset) order: pos_x[i] = number of x-items derived from all[0..i), so the
+  // item range [i0,i1) of `all` is bulk[pos_bulk[i0]..pos_bulk[i1]) etc.  Hybrid
+  // and windowed saves launch the TMA kernels over such slices.
+  std::vector<uint32_t> pos_bulk, pos_resid, pos_shift;
   std::vector<FcSpan> spans;  // source ranges by arena offset (in-place save / restore)
   cudaEvent_t ev_upload = nullptr;  // last table upload
   cudaEvent_t ev_last_use = nullptr;  // last kernel that read the tables
@@ -283,6 +484,7 @@ extern "C" int fc_ctx_create(int device, fc_ctx** out) {
   int lo = 0, hi = 0;
   cudaDeviceGetStreamPriorityRange(&lo, &hi);
   e = cudaStreamCreateWithPriority(&c->copy_stream, cudaStreamNonBlocking, hi);
+  if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&c->copy_stream2, cudaStreamNonBlocking, hi);
   cudaEvent_t* evs[] = {&c->ev_pack_start, &c->ev_pack_end,  &c->ev_drain_start, &c->ev_drain_end,
                         &c->ev_fill_start, &c->ev_fill_end,  &c->ev_scatter_end};
   for (cudaEvent_t* ev : evs)
@@ -297,6 +499,10 @@ extern "C" int fc_ctx_create(int device, fc_ctx** out) {
     if (e == cudaSuccess)
       e = cudaEventCreateWithFlags(
           &c->ring[i], cudaEventDisableTiming | (drain_spin ? 0 : cudaEventBlockingSync));
+  for (int i = 0; i < kDrainRing; ++i)
+    if (e == cudaSuccess)
+      e = cudaEventCreateWithFlags(&c->ring_pp[i], cudaEventDisableTiming | cudaEventBlockingSync);
+  if (const char* m = getenv("FC_DRAIN_MODE")) c->drain_mode = atoi(m) ? FC_DRAIN_PINGPONG : FC_DRAIN_HOST_PACED;
   if (e != cudaSuccess) {
     fc_ctx_destroy(c);
     return fail(FC_ECUDA, "fc_ctx_create: %s", cudaGetErrorString(e));
@@ -317,14 +523,32 @@ extern "C" int fc_ctx_destroy(fc_ctx* c) {
     c->pump.join();
   }
   if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
-  for (int i = 0; i < kDrainRing; ++i)
+  if (c->copy_stream2) cudaStreamSynchronize(c->copy_stream2);
+  for (int i = 0; i < kDrainRing; ++i) {
     if (c->ring[i]) cudaEventDestroy(c->ring[i]);
-  for (void* p : c->registered) cudaHostUnregister(p);
+    if (c->ring_pp[i]) cudaEventDestroy(c->ring_pp[i]);
+  }
+  for (auto& r : c->regs) {
+    r->cancel = true;
+    if (r->th.joinable()) r->th.join();
+    for (void* q : r->done) cudaHostUnregister(q);
+  }
+  c->regs.clear();
+  for (auto& w : c->stage) {
+    if (w.stream) cudaStreamSynchronize(w.stream);
+    for (int i = 0; i < 2; ++i) {
+      if (w.ev[i]) cudaEventDestroy(w.ev[i]);
+      if (w.slot[i]) cudaFreeHost(w.slot[i]);
+    }
+    if (w.stream) cudaStreamDestroy(w.stream);
+  }
+  c->stage.clear();
   cudaEvent_t evs[] = {c->ev_pack_start, c->ev_pack_end, c->ev_drain_start, c->ev_drain_end,
                        c->ev_fill_start, c->ev_fill_end, c->ev_scatter_end};
   for (cudaEvent_t ev : evs)
     if (ev) cudaEventDestroy(ev);
   if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+  if (c->copy_stream2) cudaStreamDestroy(c->copy_stream2);
   if (c->arena) cudaFree(c->arena);
   for (void* q : c->dead_dev) cudaFree(q);
   for (void* q : c->dead_pinned) cudaFreeHost(q);
@@ -415,20 +639,68 @@ static int gpu_numa_node(int device) {
 // target should be local to the GPU's socket: with 8 ranks draining at once
 // the inter-socket link would otherwise carry half of the 440 GB/s).  Applies
 // to pages not faulted in yet; best effort, failures are ignored.
-static void prefer_numa_node(void* host, uint64_t bytes, int node) {
+static void mbind_preferred(uintptr_t lo, uintptr_t hi, int node) {
 #if defined(SYS_mbind)
-  if (node < 0 || node >= 1024) return;
-  const long pg = sysconf(_SC_PAGESIZE);
-  uintptr_t lo = (uintptr_t)host & ~((uintptr_t)pg - 1);
-  uintptr_t hi = ((uintptr_t)host + bytes + pg - 1) & ~((uintptr_t)pg - 1);
+  if (node < 0 || node >= 1024 || hi <= lo) return;
   unsigned long mask[16] = {0};
   mask[node / (8 * sizeof(unsigned long))] |= 1ul << (node % (8 * sizeof(unsigned long)));
   const int kMpolPreferred = 1;
   (void)syscall(SYS_mbind, (void*)lo, (unsigned long)(hi - lo), kMpolPreferred, mask,
                 (unsigned long)(8 * sizeof(mask)), 0u);
 #else
-  (void)host; (void)bytes; (void)node;
+  (void)lo; (void)hi; (void)node;
 #endif
+}
+
+// remote_per256 > 0: of every 256 consecutive 2-MiB blocks that many (spread evenly)
+// are bound to `remote` instead of `node` — when more GPUs of one socket drain at
+// once than its memory controllers absorb and the other socket is idle, a share of
+// the DMA writes goes over the inter-socket link (profiles/r02_numa_split.md).
+static void prefer_numa_node(void* host, uint64_t bytes, int node, int remote = -1,
+                             int remote_per256 = 0) {
+  if (node < 0) return;
+  const uintptr_t pg = (uintptr_t)sysconf(_SC_PAGESIZE);
+  const uintptr_t lo = (uintptr_t)host & ~(pg - 1);
+  const uintptr_t hi = ((uintptr_t)host + bytes + pg - 1) & ~(pg - 1);
+  mbind_preferred(lo, hi, node);
+  if (remote < 0 || remote == node || remote_per256 <= 0) return;
+  if (remote_per256 > 256) remote_per256 = 256;
+  const uintptr_t blk = 2ull << 20;
+  // block k is remote iff floor((k+1)*r/256) > floor(k*r/256): evenly spread;
+  // indexed from the block number of the ADDRESS so sub-ranges registered by
+  // different processes agree on the pattern
+  for (uintptr_t a = lo & ~(blk - 1); a < hi; a += blk) {
+    const uint64_t k = (uint64_t)(a / blk);
+    if (((k + 1) * (uint64_t)remote_per256) / 256 > (k * (uint64_t)remote_per256) / 256)
+      mbind_preferred(std::max(a, lo), std::min(a + blk, hi), remote);
+  }
+}
+
+static int numa_node_count() {
+  int n = 0;
+  char path[96];
+  for (; n < 64; ++n) {
+    snprintf(path, sizeof(path), "/sys/devices/system/node/node%d", n);
+    if (access(path, F_OK) != 0) break;
+  }
+  return n;
+}
+
+extern "C" int fc_device_numa_node(int device, int* node, int* n_nodes) {
+  if (node) *node = gpu_numa_node(device);
+  if (n_nodes) *n_nodes = numa_node_count();
+  return FC_OK;
+}
+
+extern "C" int fc_host_bind_numa(fc_ctx* c, void* host, uint64_t bytes, int remote_per256) {
+  if (!c || !host || bytes == 0) return fail(FC_EINVAL, "fc_host_bind_numa: bad argument%s%s");
+  if (getenv("FC_NO_NUMA")) return FC_OK;
+  const int node = gpu_numa_node(c->device);
+  const int nn = numa_node_count();
+  int remote = -1;
+  if (remote_per256 > 0 && node >= 0 && nn == 2) remote = 1 - node;
+  prefer_numa_node(host, bytes, node, remote, remote_per256);
+  return FC_OK;
 }
 
 struct PrefaultJob {
@@ -449,10 +721,72 @@ static void* prefault_worker(void* arg) {
   return nullptr;
 }
 
-extern "C" int fc_host_register(fc_ctx* c, void* host, uint64_t bytes, int prefault_threads) {
-  if (!c || !host || bytes == 0) return fail(FC_EINVAL, "fc_host_register: bad argument%s%s");
-  FC_GUARD(c);
-  if (!getenv("FC_NO_NUMA")) prefer_numa_node(host, bytes, gpu_numa_node(c->device));
+static void prefault_range(void* host, uint64_t bytes, int prefault_threads) {
+  const long pg = sysconf(_SC_PAGESIZE);
+  int nt = std::max(1, std::min(prefault_threads, 64));
+  uint64_t per = ((bytes / nt + pg - 1) / pg) * pg;
+  if (per == 0) per = pg;
+  std::vector<pthread_t> th;
+  std::vector<PrefaultJob> jobs;
+  jobs.reserve(nt);
+  // mmap'd segments are page aligned; tolerate an unaligned start anyway
+  uint8_t* base = static_cast<uint8_t*>(host);
+  for (uint64_t o = 0; o < bytes; o += per)
+    jobs.push_back({base + o, (size_t)std::min<uint64_t>(per, bytes - o)});
+  th.resize(jobs.size());
+  for (size_t i = 0; i < jobs.size(); ++i)
+    if (pthread_create(&th[i], nullptr, prefault_worker, &jobs[i]) != 0) {
+      prefault_worker(&jobs[i]);
+      th[i] = 0;
+    }
+  for (size_t i = 0; i < jobs.size(); ++i)
+    if (th[i]) pthread_join(th[i], nullptr);
+}
+
+static fc_ctx::HostReg* find_reg(fc_ctx* c, const void* host) {
+  for (auto& r : c->regs)
+    if (r->base == host) return r.get();
+  return nullptr;
+}
+
+// The registration covering [p, p+len), or nullptr.
+static fc_ctx::HostReg* reg_covering(fc_ctx* c, const uint8_t* p, uint64_t len) {
+  for (auto& r : c->regs)
+    if (p >= r->base && p + len <= r->base + r->bytes) return r.get();
+  return nullptr;
+}
+
+// 0 when [p, p+len) lies in a completely registered range (plain DMA), else the
+// number of host threads the staged path should use.
+static int staged_threads_for(fc_ctx* c, const uint8_t* p, uint64_t len) {
+  if (len == 0 || getenv("FC_NO_STAGING")) return 0;
+  std::lock_guard<std::mutex> lk(c->mu);
+  fc_ctx::HostReg* r = reg_covering(c, p, len);
+  if (r && r->state == 1) return 0;
+  return std::max(1, c->stage_threads);
+}
+
+static void register_slices(fc_ctx* c, fc_ctx::HostReg* r) {
+  cudaSetDevice(c->device);
+  for (uint64_t o = 0; o < r->bytes && !r->cancel; o += r->slice) {
+    const uint64_t len = std::min<uint64_t>(r->slice, r->bytes - o);
+    cudaError_t e = cudaHostRegister(r->base + o, len, cudaHostRegisterPortable);
+    if (e == cudaErrorHostMemoryAlreadyRegistered) {
+      (void)cudaGetLastError();
+      continue;
+    }
+    if (e != cudaSuccess) {
+      (void)cudaGetLastError();
+      r->state = -1;
+      return;
+    }
+    std::lock_guard<std::mutex> lk(c->mu);
+    r->done.push_back(r->base + o);
+  }
+  if (!r->cancel) r->state = 1;
+}
+
+static void madvise_hugepage(void* host, uint64_t bytes) {
 #ifdef MADV_HUGEPAGE
   // 2 MiB pages where the host allows them for this mapping (tmpfs: only with
   // transparent_hugepage/shmem_enabled = advise|always): fewer IOMMU / page-table
@@ -463,27 +797,22 @@ extern "C" int fc_host_register(fc_ctx* c, void* host, uint64_t bytes, int prefa
     uintptr_t hi = ((uintptr_t)host + bytes) & ~(pg - 1);
     if (hi > lo) (void)madvise((void*)lo, hi - lo, MADV_HUGEPAGE);
   }
+#else
+  (void)host; (void)bytes;
 #endif
-  if (prefault_threads > 0) {
-    const long pg = sysconf(_SC_PAGESIZE);
-    int nt = std::min(prefault_threads, 64);
-    uint64_t per = ((bytes / nt + pg - 1) / pg) * pg;
-    if (per == 0) per = pg;
-    std::vector<pthread_t> th;
-    std::vector<PrefaultJob> jobs;
-    jobs.reserve(nt);
-    // mmap'd segments are page aligned; tolerate an unaligned start anyway
-    uint8_t* base = static_cast<uint8_t*>(host);
-    for (uint64_t o = 0; o < bytes; o += per) jobs.push_back({base + o, (size_t)std::min<uint64_t>(per, bytes - o)});
-    th.resize(jobs.size());
-    for (size_t i = 0; i < jobs.size(); ++i)
-      if (pthread_create(&th[i], nullptr, prefault_worker, &jobs[i]) != 0) {
-        prefault_worker(&jobs[i]);
-        th[i] = 0;
-      }
-    for (size_t i = 0; i < jobs.size(); ++i)
-      if (th[i]) pthread_join(th[i], nullptr);
+}
+
+extern "C" int fc_host_register(fc_ctx* c, void* host, uint64_t bytes, int prefault_threads) {
+  if (!c || !host || bytes == 0) return fail(FC_EINVAL, "fc_host_register: bad argument%s%s");
+  FC_GUARD(c);
+  if (fc_ctx::HostReg* old = find_reg(c, host)) {
+    if (old->th.joinable()) old->th.join();  // a background registration: let it finish
+    if (old->state == 1 && old->bytes >= bytes) return FC_OK;
+    return fail(FC_EINVAL, "fc_host_register: range already known with another size%s%s");
   }
+  if (!getenv("FC_NO_NUMA")) prefer_numa_node(host, bytes, gpu_numa_node(c->device));
+  madvise_hugepage(host, bytes);
+  if (prefault_threads > 0) prefault_range(host, bytes, prefault_threads);
   cudaError_t e = cudaHostRegister(host, bytes, cudaHostRegisterPortable);
   if (e == cudaErrorHostMemoryAlreadyRegistered) {
     (void)cudaGetLastError();
@@ -493,23 +822,78 @@ extern "C" int fc_host_register(fc_ctx* c, void* host, uint64_t bytes, int prefa
     (void)cudaGetLastError();
     return fail(FC_ECUDA, "cudaHostRegister: %s", cudaGetErrorString(e));
   }
-  c->registered.push_back(host);
+  std::unique_ptr<fc_ctx::HostReg> r(new fc_ctx::HostReg());
+  r->base = static_cast<uint8_t*>(host);
+  r->bytes = bytes;
+  r->done.push_back(host);
+  r->state = 1;
+  std::lock_guard<std::mutex> lk(c->mu);
+  c->regs.push_back(std::move(r));
   return FC_OK;
+}
+
+extern "C" int fc_host_register_background(fc_ctx* c, void* host, uint64_t bytes,
+                                           uint64_t slice_bytes) {
+  if (!c || !host || bytes == 0)
+    return fail(FC_EINVAL, "fc_host_register_background: bad argument%s%s");
+  if (find_reg(c, host)) return FC_OK;  // known: in progress or done
+  const uint64_t pg = (uint64_t)sysconf(_SC_PAGESIZE);
+  if (slice_bytes == 0) slice_bytes = 64ull << 20;
+  slice_bytes = std::max<uint64_t>((slice_bytes + pg - 1) / pg * pg, 2ull << 20);
+  std::unique_ptr<fc_ctx::HostReg> r(new fc_ctx::HostReg());
+  r->base = static_cast<uint8_t*>(host);
+  r->bytes = bytes;
+  r->slice = slice_bytes;
+  fc_ctx::HostReg* raw = r.get();
+  {
+    std::lock_guard<std::mutex> lk(c->mu);
+    c->regs.push_back(std::move(r));
+  }
+  raw->th = std::thread(register_slices, c, raw);
+  return FC_OK;
+}
+
+extern "C" int fc_host_ready(fc_ctx* c, const void* host) {
+  if (!c || !host) return fail(FC_EINVAL, "fc_host_ready: bad argument%s%s");
+  fc_ctx::HostReg* r = find_reg(c, host);
+  if (!r) return fail(FC_EINVAL, "fc_host_ready: unknown host range%s%s");
+  const int st = r->state;
+  if (st == 1) return FC_OK;
+  if (st == 0) return FC_ENOTREADY;
+  return fail(FC_ECUDA, "background cudaHostRegister failed%s%s");
 }
 
 extern "C" int fc_host_unregister(fc_ctx* c, void* host) {
   if (!c || !host) return fail(FC_EINVAL, "fc_host_unregister: bad argument%s%s");
   FC_GUARD(c);
-  auto it = std::find(c->registered.begin(), c->registered.end(), host);
-  if (it == c->registered.end()) return FC_OK;
+  fc_ctx::HostReg* r = find_reg(c, host);
+  if (!r) return FC_OK;
+  r->cancel = true;
+  if (r->th.joinable()) r->th.join();
   // no DMA may still target the range: let the pump finish, then the stream
   {
     std::unique_lock<std::mutex> lk(c->mu);
     c->cv.wait(lk, [&] { return c->drained_ticket >= c->ticket; });
   }
   FC_CUDA(cudaStreamSynchronize(c->copy_stream));
-  c->registered.erase(it);
-  FC_CUDA(cudaHostUnregister(host));
+  if (c->copy_stream2) FC_CUDA(cudaStreamSynchronize(c->copy_stream2));
+  cudaError_t first = cudaSuccess;
+  for (void* q : r->done) {
+    cudaError_t e = cudaHostUnregister(q);
+    if (e != cudaSuccess && first == cudaSuccess) first = e;
+  }
+  {
+    std::lock_guard<std::mutex> lk(c->mu);
+    for (auto it = c->regs.begin(); it != c->regs.end(); ++it)
+      if (it->get() == r) {
+        c->regs.erase(it);
+        break;
+      }
+  }
+  if (first != cudaSuccess) {
+    (void)cudaGetLastError();
+    return fail(FC_ECUDA, "cudaHostUnregister: %s", cudaGetErrorString(first));
+  }
   return FC_OK;
 }
 
@@ -605,29 +989,52 @@ static int plan_fill(fc_plan* p, uint32_t n, const void* const* dev_ptrs,
 
   std::vector<FcItem> all, bulk, resid, shift;
   for (uint32_t i = 0; i < n; ++i) {
-    uint64_t nb = nbytes[i];
-    if (nb == 0) continue;
-    uint64_t tp = (uint64_t)(uintptr_t)dev_ptrs[i];
-    uint64_t off = arena_off[i];
-    split_range(all, tp, off, nb, chunk_bytes);
-    if (((tp - off) & 15u) != 0) {  // not congruent mod 16: byte-shift path
-      // small ranges are not worth a TMA tile: leave them to the LSU kernel
-      if (nb < 4096)
-        split_range(resid, tp, off, nb, chunk_bytes);
-      else
-        split_range(shift, tp, off, nb, chunk_bytes);
-      continue;
-    }
-    uint64_t head = std::min<uint64_t>((16u - (off & 15u)) & 15u, nb);
-    if (head) split_range(resid, tp, off, head, chunk_bytes);
-    uint64_t body = (nb - head) & ~15ull;
-    if (body) split_range(bulk, tp + head, off + head, body, chunk_bytes);
-    uint64_t tail = nb - head - body;
-    if (tail) split_range(resid, tp + head + body, off + head + body, tail, chunk_bytes);
+    if (nbytes[i] == 0) continue;
+    split_range(all, (uint64_t)(uintptr_t)dev_ptrs[i], arena_off[i], nbytes[i], chunk_bytes);
   }
   if (all.size() > 0xFFFFFFF0ull) return fail(FC_EINVAL, "plan: too many work items%s%s");
   std::stable_sort(all.begin(), all.end(),
                    [](const FcItem& a, const FcItem& b) { return a.aoff < b.aoff; });
+  // Derive the TMA-variant tables from `all`, item by item.  Interior item
+  // boundaries are 128-B aligned in arena space, so a head (< 16 B) only exists at
+  // the start of a range and a tail only at its end.
+  std::vector<uint32_t> pos_bulk(all.size() + 1), pos_resid(all.size() + 1),
+      pos_shift(all.size() + 1);
+  for (size_t k = 0; k < all.size(); ++k) {
+    pos_bulk[k] = (uint32_t)bulk.size();
+    pos_resid[k] = (uint32_t)resid.size();
+    pos_shift[k] = (uint32_t)shift.size();
+    const FcItem& it = all[k];
+    const uint64_t tp = it.tptr, off = it.aoff, nb = it.nbytes;
+    if (((tp - off) & 15u) != 0) {  // not congruent mod 16: byte-shift path
+      // pieces too small for a TMA tile go to the LSU kernel
+      (nb < 4096 ? resid : shift).push_back(it);
+      continue;
+    }
+    const uint64_t head = std::min<uint64_t>((16u - (off & 15u)) & 15u, nb);
+    const uint64_t body = (nb - head) & ~15ull;
+    const uint64_t tail = nb - head - body;
+    FcItem piece = it;
+    if (head) {
+      piece.nbytes = (uint32_t)head;
+      resid.push_back(piece);
+    }
+    if (body) {
+      piece.tptr = tp + head;
+      piece.aoff = off + head;
+      piece.nbytes = (uint32_t)body;
+      bulk.push_back(piece);
+    }
+    if (tail) {
+      piece.tptr = tp + head + body;
+      piece.aoff = off + head + body;
+      piece.nbytes = (uint32_t)tail;
+      resid.push_back(piece);
+    }
+  }
+  pos_bulk[all.size()] = (uint32_t)bulk.size();
+  pos_resid[all.size()] = (uint32_t)resid.size();
+  pos_shift[all.size()] = (uint32_t)shift.size();
   int rc = table_set(c, p->all, all, s, sync);
   if (!rc) rc = table_set(c, p->bulk, bulk, s, sync);
   if (!rc) rc = table_set(c, p->resid, resid, s, sync);
@@ -637,6 +1044,9 @@ static int plan_fill(fc_plan* p, uint32_t n, const void* const* dev_ptrs,
   p->arena_end = arena_end;
   p->runs.swap(runs);
   p->h_all.swap(all);
+  p->pos_bulk.swap(pos_bulk);
+  p->pos_resid.swap(pos_resid);
+  p->pos_shift.swap(pos_shift);
   std::sort(spans.begin(), spans.end(),
             [](const FcSpan& a, const FcSpan& b) { return a.off < b.off; });
   // NOT merged even where tensor and arena addresses both continue: two tensors may
@@ -762,23 +1172,23 @@ extern "C" int fc_set_launch(fc_ctx* c, int lsu_ctas_per_sm, int tma_ctas_per_sm
 }
 
 template <int DIR>
-static int launch_lsu(fc_ctx* c, const FcItem* items, uint32_t n, cudaStream_t s) {
+static int launch_lsu(fc_ctx* c, const FcItem* items, uint32_t n, uint8_t* arena, cudaStream_t s) {
   if (n == 0) return FC_OK;
   uint32_t grid = std::min<uint32_t>(n, (uint32_t)(c->sm_count * c->lsu_ctas_per_sm));
-  fc_copy_lsu<DIR><<<grid, kLsuThreads, 0, s>>>(items, n, c->arena);
+  fc_copy_lsu<DIR><<<grid, kLsuThreads, 0, s>>>(items, n, arena);
   FC_CUDA(cudaGetLastError());
   c->n_kernels += 1;
   return FC_OK;
 }
 
 template <int DIR>
-static int launch_tma(fc_ctx* c, const FcItem* items, uint32_t n, cudaStream_t s) {
+static int launch_tma(fc_ctx* c, const FcItem* items, uint32_t n, uint8_t* arena, cudaStream_t s) {
   if (n == 0) return FC_OK;
   const size_t smem = (size_t)c->tma_stages * c->tma_tile + 8u * c->tma_stages;
   FC_CUDA(cudaFuncSetAttribute(fc_copy_tma<DIR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                (int)smem));
   uint32_t grid = std::min<uint32_t>(n, (uint32_t)(c->sm_count * c->tma_ctas_per_sm));
-  fc_copy_tma<DIR><<<grid, 32, smem, s>>>(items, n, c->arena, (uint32_t)c->tma_tile,
+  fc_copy_tma<DIR><<<grid, 32, smem, s>>>(items, n, arena, (uint32_t)c->tma_tile,
                                            (uint32_t)c->tma_stages);
   FC_CUDA(cudaGetLastError());
   c->n_kernels += 1;
@@ -786,17 +1196,48 @@ static int launch_tma(fc_ctx* c, const FcItem* items, uint32_t n, cudaStream_t s
 }
 
 template <int DIR>
-static int launch_shift(fc_ctx* c, const FcItem* items, uint32_t n, cudaStream_t s) {
+static int launch_shift(fc_ctx* c, const FcItem* items, uint32_t n, uint8_t* arena,
+                        cudaStream_t s) {
   if (n == 0) return FC_OK;
   const size_t smem = shift_smem_bytes((uint32_t)c->shift_tile, (uint32_t)c->shift_stages);
   FC_CUDA(cudaFuncSetAttribute(fc_copy_tma_shift<DIR>,
                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   uint32_t grid = std::min<uint32_t>(n, (uint32_t)(c->sm_count * c->shift_ctas_per_sm));
   fc_copy_tma_shift<DIR><<<grid, kShiftThreads, smem, s>>>(
-      items, n, c->arena, (uint32_t)c->shift_tile, (uint32_t)c->shift_stages);
+      items, n, arena, (uint32_t)c->shift_tile, (uint32_t)c->shift_stages);
   FC_CUDA(cudaGetLastError());
   c->n_kernels += 1;
   return FC_OK;
+}
+
+// Where arena byte 0 stands when only the part of a plan at and above segment offset
+// `lo` is staged: rounded down to 128 B so that every item keeps its alignment class
+// (mod 16 congruence, 128-B interior boundaries) and the same tables apply.
+static inline uint64_t arena_base_for(uint64_t lo) { return lo & ~127ull; }
+
+// Copy the items [i0, i1) of the offset-sorted `all` table (both directions), the
+// arena's byte 0 standing for segment offset `base` (a multiple of 128).
+template <int DIR>
+static int launch_slice(fc_plan* p, cudaStream_t s, int variant, uint32_t i0, uint32_t i1,
+                        uint64_t base) {
+  fc_ctx* c = p->ctx;
+  if (i1 <= i0) return FC_OK;
+  if (variant == FC_VARIANT_AUTO) variant = c->variant;
+  uint8_t* arena = c->arena - base;  // the kernels add the item's absolute offset
+  int rc;
+  if (variant == FC_VARIANT_TMA) {
+    rc = launch_tma<DIR>(c, p->bulk.dev + p->pos_bulk[i0], p->pos_bulk[i1] - p->pos_bulk[i0],
+                         arena, s);
+    if (!rc)
+      rc = launch_shift<DIR>(c, p->shift.dev + p->pos_shift[i0],
+                             p->pos_shift[i1] - p->pos_shift[i0], arena, s);
+    if (!rc)
+      rc = launch_lsu<DIR>(c, p->resid.dev + p->pos_resid[i0],
+                           p->pos_resid[i1] - p->pos_resid[i0], arena, s);
+  } else {
+    rc = launch_lsu<DIR>(c, p->all.dev + i0, i1 - i0, arena, s);
+  }
+  return rc;
 }
 
 template <int DIR>
@@ -804,17 +1245,9 @@ static int launch_copy(fc_plan* p, cudaStream_t s, int variant) {
   fc_ctx* c = p->ctx;
   if (p->arena_end > c->arena_bytes)
     return fail(FC_EINVAL, "arena smaller than the plan: call fc_arena_reserve first%s%s");
-  if (variant == FC_VARIANT_AUTO) variant = c->variant;
   // tables may have been (re)uploaded on another stream
   FC_CUDA(cudaStreamWaitEvent(s, p->ev_upload, 0));
-  int rc;
-  if (variant == FC_VARIANT_TMA) {
-    rc = launch_tma<DIR>(c, p->bulk.dev, p->bulk.n, s);
-    if (!rc) rc = launch_shift<DIR>(c, p->shift.dev, p->shift.n, s);
-    if (!rc) rc = launch_lsu<DIR>(c, p->resid.dev, p->resid.n, s);
-  } else {
-    rc = launch_lsu<DIR>(c, p->all.dev, p->all.n, s);
-  }
+  int rc = launch_slice<DIR>(p, s, variant, 0, p->all.n, 0);
   if (rc) return rc;
   FC_CUDA(cudaEventRecord(p->ev_last_use, s));
   return FC_OK;
@@ -842,7 +1275,8 @@ extern "C" int fc_unpack_async(fc_plan* p, void* stream, int variant) {
 // reference's behaviour, at PCIe instead of pageable-copy speed.
 struct Window {
   uint32_t i0, i1;      // item index range in h_all / d_all
-  uint64_t base, end;   // arena byte range covered
+  uint64_t base, end;   // segment byte range covered
+  uint64_t abase;       // segment offset arena byte 0 stands for (base rounded down to 128)
 };
 
 static std::vector<Window> make_windows(const fc_plan* p, uint64_t arena_bytes) {
@@ -850,8 +1284,8 @@ static std::vector<Window> make_windows(const fc_plan* p, uint64_t arena_bytes) 
   const std::vector<FcItem>& it = p->h_all;
   uint32_t i = 0, n = (uint32_t)it.size();
   while (i < n) {
-    Window cur{i, i, it[i].aoff, it[i].aoff};
-    while (cur.i1 < n && it[cur.i1].aoff + it[cur.i1].nbytes - cur.base <= arena_bytes) {
+    Window cur{i, i, it[i].aoff, it[i].aoff, arena_base_for(it[i].aoff)};
+    while (cur.i1 < n && it[cur.i1].aoff + it[cur.i1].nbytes - cur.abase <= arena_bytes) {
       cur.end = std::max<uint64_t>(cur.end, it[cur.i1].aoff + it[cur.i1].nbytes);
       ++cur.i1;
     }
@@ -892,19 +1326,15 @@ static int save_windowed(fc_plan* p, uint8_t* host, cudaStream_t cs) {
   FC_CUDA(cudaEventRecord(c->ev_pack_start, cs));
   bool first = true;
   for (const Window& w : wins) {
-    // arena - base: the kernel adds the item's absolute arena offset
-    uint32_t n = w.i1 - w.i0;
-    uint32_t grid = std::min<uint32_t>(n, (uint32_t)(c->sm_count * c->lsu_ctas_per_sm));
-    fc_copy_lsu<0><<<grid, kLsuThreads, 0, cs>>>(p->all.dev + w.i0, n, c->arena - w.base);
-    FC_CUDA(cudaGetLastError());
-    c->n_kernels += 1;
+    int rc = launch_slice<0>(p, cs, FC_VARIANT_AUTO, w.i0, w.i1, w.abase);
+    if (rc) return rc;
     FC_CUDA(cudaEventRecord(c->ev_pack_end, cs));
     FC_CUDA(cudaStreamWaitEvent(c->copy_stream, c->ev_pack_end, 0));
     if (first) {
       FC_CUDA(cudaEventRecord(c->ev_drain_start, c->copy_stream));
       first = false;
     }
-    int rc = copy_window<true>(c, p, host, w.base, w.end, w.base);
+    rc = copy_window<true>(c, p, host, w.base, w.end, w.abase);
     if (rc) return rc;
     // the next gather overwrites the window: it must wait for this drain
     FC_CUDA(cudaEventRecord(c->ev_drain_end, c->copy_stream));
@@ -927,15 +1357,12 @@ static int restore_windowed(fc_plan* p, const uint8_t* host, cudaStream_t s) {
   FC_CUDA(cudaStreamWaitEvent(s, p->ev_upload, 0));
   FC_CUDA(cudaEventRecord(c->ev_fill_start, c->copy_stream));
   for (const Window& w : wins) {
-    int rc = copy_window<false>(c, p, const_cast<uint8_t*>(host), w.base, w.end, w.base);
+    int rc = copy_window<false>(c, p, const_cast<uint8_t*>(host), w.base, w.end, w.abase);
     if (rc) return rc;
     FC_CUDA(cudaEventRecord(c->ev_fill_end, c->copy_stream));
     FC_CUDA(cudaStreamWaitEvent(s, c->ev_fill_end, 0));
-    uint32_t n = w.i1 - w.i0;
-    uint32_t grid = std::min<uint32_t>(n, (uint32_t)(c->sm_count * c->lsu_ctas_per_sm));
-    fc_copy_lsu<1><<<grid, kLsuThreads, 0, s>>>(p->all.dev + w.i0, n, c->arena - w.base);
-    FC_CUDA(cudaGetLastError());
-    c->n_kernels += 1;
+    rc = launch_slice<1>(p, s, FC_VARIANT_AUTO, w.i0, w.i1, w.abase);
+    if (rc) return rc;
     FC_CUDA(cudaEventRecord(c->ev_scatter_end, s));
     FC_CUDA(cudaEventSynchronize(c->ev_scatter_end));  // window is reused by the next fill
   }
@@ -1007,10 +1434,19 @@ static int save_async_impl(fc_plan* p, void* host_base, void* compute_stream, ui
     if (ticket) *ticket = c->ticket;
     return FC_OK;
   }
+  {
+    // a sticky drain error must surface BEFORE the arena is overwritten
+    std::lock_guard<std::mutex> lk(c->mu);
+    if (c->drain_rc != FC_OK) return fail(c->drain_rc, "%s", c->drain_err.c_str());
+  }
   FC_CUDA(cudaEventRecord(c->ev_pack_start, cs));
   rc = launch_copy<0>(p, cs, FC_VARIANT_AUTO);
   if (rc) return rc;
   FC_CUDA(cudaEventRecord(c->ev_pack_end, cs));
+  const int staged =
+      p->runs.empty() ? 0
+                      : staged_threads_for(c, static_cast<uint8_t*>(host_base) + p->runs.front().off,
+                                           p->arena_end - p->runs.front().off);
   // hand the drain to the pump thread (paced submission, see kDrainPiece)
   {
     std::lock_guard<std::mutex> lk(c->mu);
@@ -1018,6 +1454,7 @@ static int save_async_impl(fc_plan* p, void* host_base, void* compute_stream, ui
     if (!c->pump.joinable()) c->pump = std::thread(pump_main, c);
     c->ticket += 1;
     fc_ctx::DrainJob job;
+    job.staged_threads = staged;
     job.host = static_cast<uint8_t*>(host_base);
     job.runs = p->runs;
     job.ticket = c->ticket;
@@ -1031,8 +1468,9 @@ static int save_async_impl(fc_plan* p, void* host_base, void* compute_stream, ui
 }
 
 // In-place part below `cut` (DMA from the tensors, drained first), snapshot part at
-// and above it (LSU gather over a slice of the offset-sorted table into the arena,
-// whose byte 0 stands for segment offset `cut`).
+// and above it: the same bulk/shift/resid kernels as a full save, over the table
+// slices from the cut on, into the arena whose byte 0 stands for segment offset
+// `cut` rounded down to 128 B.
 static int save_hybrid_impl(fc_plan* p, void* host_base, void* compute_stream, uint64_t cut,
                             int hold, uint64_t* ticket) {
   if (!p || (!host_base && p->payload))
@@ -1051,27 +1489,35 @@ static int save_hybrid_impl(fc_plan* p, void* host_base, void* compute_stream, u
                            it.begin());
   if (i0 > 0 && it[i0 - 1].aoff + it[i0 - 1].nbytes > cut)
     return fail(FC_EINVAL, "fc_save_hybrid_async: cut is not a tensor boundary%s%s");
-  if (i0 < n && p->arena_end - cut > c->arena_bytes)
+  const uint64_t abase = arena_base_for(std::min(cut, p->arena_end));
+  if (i0 < n && p->arena_end - abase > c->arena_bytes)
     return fail(FC_EINVAL, "fc_save_hybrid_async: arena smaller than the snapshot part%s%s");
+  {
+    // a sticky drain error must surface BEFORE the arena is overwritten
+    std::lock_guard<std::mutex> lk(c->mu);
+    if (c->drain_rc != FC_OK) return fail(c->drain_rc, "%s", c->drain_err.c_str());
+  }
   // with no kernel the pair of events still orders the drain after everything
   // already queued on the training stream (the optimizer step that produced the values)
   FC_CUDA(cudaEventRecord(c->ev_pack_start, cs));
   if (i0 < n) {
     FC_CUDA(cudaStreamWaitEvent(cs, p->ev_upload, 0));
-    uint32_t m = n - i0;
-    uint32_t grid = std::min<uint32_t>(m, (uint32_t)(c->sm_count * c->lsu_ctas_per_sm));
-    fc_copy_lsu<0><<<grid, kLsuThreads, 0, cs>>>(p->all.dev + i0, m, c->arena - cut);
-    FC_CUDA(cudaGetLastError());
-    c->n_kernels += 1;
+    rc = launch_slice<0>(p, cs, FC_VARIANT_AUTO, i0, n, abase);
+    if (rc) return rc;
     FC_CUDA(cudaEventRecord(p->ev_last_use, cs));
   }
   FC_CUDA(cudaEventRecord(c->ev_pack_end, cs));
+  const int staged =
+      p->runs.empty() ? 0
+                      : staged_threads_for(c, static_cast<uint8_t*>(host_base) + p->runs.front().off,
+                                           p->arena_end - p->runs.front().off);
   {
     std::lock_guard<std::mutex> lk(c->mu);
     if (c->drain_rc != FC_OK) return fail(c->drain_rc, "%s", c->drain_err.c_str());
     if (!c->pump.joinable()) c->pump = std::thread(pump_main, c);
     c->ticket += 1;
     fc_ctx::DrainJob job;
+    job.staged_threads = staged;
     job.host = static_cast<uint8_t*>(host_base);
     for (const FcSpan& sp : p->spans)
       if (sp.off < cut) job.spans.push_back(sp);
@@ -1080,7 +1526,7 @@ static int save_hybrid_impl(fc_plan* p, void* host_base, void* compute_stream, u
       if (b > a) job.runs.push_back({a, b - a});
     }
     job.direct = true;
-    job.arena_base = cut;
+    job.arena_base = abase;
     job.ticket = c->ticket;
     if (hold) c->held_ticket = c->ticket;
     c->direct_ticket = c->ticket;
@@ -1117,6 +1563,25 @@ extern "C" int fc_restore_direct_async(fc_plan* p, const void* host_base, void* 
   FC_CUDA(cudaEventRecord(c->ev_scatter_end, s));
   FC_CUDA(cudaStreamWaitEvent(c->copy_stream, c->ev_scatter_end, 0));
   FC_CUDA(cudaEventRecord(c->ev_fill_start, c->copy_stream));
+  const int staged =
+      p->spans.empty() ? 0
+                       : staged_threads_for(c, hb + p->spans.front().off,
+                                            p->arena_end - p->spans.front().off);
+  if (staged > 0) {
+    // unregistered segment (a restarted trainer): bounce slots, blocks until the data
+    // is on the device
+    std::vector<StagePiece> pieces;
+    for (const FcSpan& sp : p->spans)
+      stage_pieces(pieces, (uint8_t*)(uintptr_t)sp.tptr, const_cast<uint8_t*>(hb) + sp.off,
+                   sp.len, c->stage_slot);
+    cudaError_t e = stage_run(c, pieces, false, c->ev_scatter_end, staged);
+    if (e != cudaSuccess) return fail(FC_ECUDA, "staged restore: %s", cudaGetErrorString(e));
+    c->n_memcpys += pieces.size();
+    FC_CUDA(cudaEventRecord(c->ev_fill_end, c->copy_stream));
+    FC_CUDA(cudaEventRecord(c->ev_scatter_end, s));
+    c->restore_inflight = true;
+    return FC_OK;
+  }
   for (const FcSpan& sp : p->spans)
     for (uint64_t o = 0; o < sp.len; o += kDmaPiece) {
       uint64_t len = std::min<uint64_t>(kDmaPiece, sp.len - o);
@@ -1239,6 +1704,27 @@ extern "C" int fc_set_drain(fc_ctx* c, uint64_t piece_bytes, int depth) {
   return FC_OK;
 }
 
+extern "C" int fc_set_stage(fc_ctx* c, int threads, uint64_t slot_bytes) {
+  if (!c || threads < 0 || threads > 32 || (slot_bytes && slot_bytes < (256u << 10)) ||
+      slot_bytes > (256ull << 20))
+    return fail(FC_EINVAL, "fc_set_stage: threads in [1, 32], slot in [256 KiB, 256 MiB]%s%s");
+  std::lock_guard<std::mutex> lk(c->mu);
+  if (threads) c->stage_threads = threads;
+  if (slot_bytes && slot_bytes != c->stage_slot) {
+    if (!c->stage.empty()) return fail(FC_EBUSY, "fc_set_stage: slots already allocated%s%s");
+    c->stage_slot = slot_bytes;
+  }
+  return FC_OK;
+}
+
+extern "C" int fc_set_drain_mode(fc_ctx* c, int mode) {
+  if (!c || (mode != FC_DRAIN_HOST_PACED && mode != FC_DRAIN_PINGPONG))
+    return fail(FC_EINVAL, "fc_set_drain_mode: bad argument%s%s");
+  std::lock_guard<std::mutex> lk(c->mu);
+  c->drain_mode = mode;
+  return FC_OK;
+}
+
 // ---- host-resident leaves ---------------------------------------------------
 // CPU tensors inside a state_dict (optimizer step counters, RNG state, a whole
 // CPU model in the gloo/CPU configuration) are already in host memory: they go
@@ -1352,6 +1838,25 @@ extern "C" int fc_restore_async(fc_plan* p, const void* host_base, void* stream)
   cudaStream_t s = (cudaStream_t)stream;
   const uint8_t* hb = static_cast<const uint8_t*>(host_base);
   FC_CUDA(cudaEventRecord(c->ev_fill_start, c->copy_stream));
+  const int staged =
+      p->runs.empty() ? 0
+                      : staged_threads_for(c, hb + p->runs.front().off,
+                                           p->arena_end - p->runs.front().off);
+  if (staged > 0) {
+    std::vector<StagePiece> pieces;
+    for (const FcRun& r : p->runs)
+      stage_pieces(pieces, c->arena + r.off, const_cast<uint8_t*>(hb) + r.off, r.len,
+                   c->stage_slot);
+    cudaError_t e = stage_run(c, pieces, false, nullptr, staged);
+    if (e != cudaSuccess) return fail(FC_ECUDA, "staged restore: %s", cudaGetErrorString(e));
+    c->n_memcpys += pieces.size();
+    FC_CUDA(cudaEventRecord(c->ev_fill_end, c->copy_stream));
+    rc = launch_copy<1>(p, s, FC_VARIANT_AUTO);  // the fill has completed on the host side
+    if (rc) return rc;
+    FC_CUDA(cudaEventRecord(c->ev_scatter_end, s));
+    c->restore_inflight = true;
+    return FC_OK;
+  }
   for (const FcRun& r : p->runs)
     for (uint64_t o = 0; o < r.len; o += kDmaPiece) {
       uint64_t len = std::min<uint64_t>(kDmaPiece, r.len - o);

@@ -496,10 +496,20 @@ class FsdpCheckpointEngine(CheckpointEngine):
             if acquired:
                 self._shm_lock.release()
 
+        def failed():
+            # the segment is torn: the meta keeps writing_shm=True (the agent and a
+            # restarted trainer refuse it); only the lock goes back so later saves run
+            if acquired:
+                self._shm_lock.release()
+
         drain = self._shm_writer.pending
         if drain is None or drain.done():
-            if drain is not None:
-                drain.wait()
+            try:
+                if drain is not None:
+                    drain.wait()  # re-raises a drain error
+            except BaseException:
+                failed()
+                raise
             completed()
         else:
             import threading
@@ -507,8 +517,11 @@ class FsdpCheckpointEngine(CheckpointEngine):
             def waiter():
                 try:
                     drain.wait()
-                finally:
-                    completed()
+                except BaseException as e:
+                    logger.error(f"FSDP shard drain of step {conf.step} failed: {e}")
+                    failed()
+                    return
+                completed()
 
             threading.Thread(target=waiter, name="fc-fsdp-drain", daemon=True).start()
             self._finalizer = waiter

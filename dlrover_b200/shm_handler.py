@@ -26,6 +26,7 @@ fallback for CUDA leaves: a missing library raises.
 from __future__ import annotations
 
 import atexit
+import copy
 import json
 import os
 import threading
@@ -110,6 +111,10 @@ class _Layout:
         self.reused = 0  # leaves whose TensorMeta was taken over from `prev`
 
 
+_IMMUTABLE_LEAVES = frozenset({int, float, str, bool, bytes, type(None), complex, torch.dtype,
+                               torch.Size, torch.device})
+
+
 def plan_layout(state_dict, prev: Optional["_Layout"] = None) -> _Layout:
     """Assign every tensor leaf its byte offset (reference layout,
     ckpt_saver.py:286-301) and sort the leaves into device-resident and
@@ -148,7 +153,16 @@ def plan_layout(state_dict, prev: Optional["_Layout"] = None) -> _Layout:
             return {k: walk(v) for k, v in value.items()}
         if kind is list or isinstance(value, list):
             return [walk(v) for v in value]
-        return value  # non-tensor leaf (tuples included): carried in the meta tree
+        # non-tensor leaf (tuples included): carried in the meta tree.  The tree is
+        # pickled later, possibly on the completion thread: mutable leaves (an args
+        # Namespace, user objects) are copied NOW, on the calling thread, so they are
+        # captured from the same iteration as the tensors
+        if kind in _IMMUTABLE_LEAVES:
+            return value
+        try:
+            return copy.deepcopy(value)
+        except Exception:
+            return value
 
     lay.meta = walk(state_dict)
     lay.total = total
@@ -203,58 +217,187 @@ def _host_threads() -> int:
 # -------------------------------------------------------------- device staging --
 
 
+def _numa_remote_share(device_index: int) -> int:
+    """Of every 256 2-MiB blocks of the segment, how many to place on the OTHER socket.
+    DLROVER_B200_NUMA_REMOTE_PER256 forces a value; "auto" derives it from how the local
+    ranks' GPUs are spread over the two sockets (a ranks here, b there, a > b: (a-b)/(2a)
+    of this rank's pages go across) — see profiles/r02_numa_split.md for when it pays."""
+    env = os.getenv("DLROVER_B200_NUMA_REMOTE_PER256", "0").strip().lower()
+    if env != "auto":
+        try:
+            return max(0, min(256, int(env or 0)))
+        except ValueError:
+            return 0
+    try:
+        local_world = int(os.getenv("LOCAL_WORLD_SIZE", "1") or 1)
+        mine, n_nodes = native.device_numa_node(device_index)
+        if n_nodes != 2 or mine < 0 or local_world < 3:
+            return 0
+        here = sum(1 for d in range(local_world) if native.device_numa_node(d)[0] == mine)
+        there = local_world - here
+        if here < 3 or here <= there:
+            return 0
+        return int(256 * (here - there) / (2 * here))
+    except Exception:
+        return 0
+
+
+def _row_ranges(t: torch.Tensor, off: int, max_rows: int = 1 << 16, min_row_bytes: int = 256):
+    """A non-contiguous tensor whose trailing dims are dense ("row-strided": w[:, :k],
+    w[::2], a transposed-then-sliced view...) as one (ptr, offset, nbytes) range per dense
+    row, in logical (row-major) order — exactly the bytes `shm.copy_(t)` deposits
+    (reference ckpt_saver.py:228-231) without a device-side .contiguous() copy.
+    None when the rows would be too many / too small (the caller repacks then)."""
+    es = t.element_size()
+    sizes, strides = list(t.shape), list(t.stride())
+    k = len(sizes)  # dims [k:] form the dense row
+    expect = 1
+    while k > 0 and (sizes[k - 1] == 1 or strides[k - 1] == expect):
+        expect *= sizes[k - 1]
+        k -= 1
+    row_bytes = expect * es
+    n_rows = 1
+    for d in range(k):
+        n_rows *= sizes[d]
+    if k == 0 or row_bytes < min_row_bytes or n_rows > max_rows or any(
+            st < 0 for st in strides[:k]):
+        return None
+    base = t.data_ptr()
+    out = []
+    idx = [0] * k
+    for r in range(n_rows):
+        elem = 0
+        for d in range(k):
+            elem += idx[d] * strides[d]
+        out.append((base + elem * es, off + r * row_bytes, row_bytes))
+        for d in range(k - 1, -1, -1):
+            idx[d] += 1
+            if idx[d] < sizes[d]:
+                break
+            idx[d] = 0
+    return out
+
+
+def _clip_ranges(prepared, lo: int, hi: int):
+    """The parts of (ptrs, offsets, lengths) that fall into segment bytes [lo, hi)."""
+    ptrs, offs, lens = [], [], []
+    for p, o, n in zip(*prepared):
+        a, b = max(o, lo), min(o + n, hi)
+        if b > a:
+            ptrs.append(p + (a - o))
+            offs.append(a)
+            lens.append(b - a)
+    return ptrs, offs, lens
+
+
 class _DeviceStager:
     """Owns the libflashckpt context usage for ONE segment: host registration,
     arena sizing and the cached plan."""
 
+    # segments up to this size are pinned inline (tens of ms); larger ones are pinned
+    # by a library thread after the first transfer, which goes through bounce slots
+    SYNC_PIN_MAX = 256 << 20
+
     def __init__(self, device_index: int):
         self.device_index = device_index
         self.ctx = native.get_context(device_index)
-        self._registered_addr = 0
+        self._attached: Optional[Tuple[int, int]] = None  # (address, bytes) of our window
+        self._pin_started = False
         self._plans: Dict[str, native.Plan] = {}  # role -> plan
         self.register_seconds = 0.0
         self._warned_no_arena = False
 
-    def attach(self, shm: SharedMemory):
-        addr = shm.address
-        if addr == self._registered_addr:
+    @staticmethod
+    def _pin_mode() -> str:
+        # "background" (default) | "sync" (pin inline, as round 1 did) | "none"
+        return os.getenv("DLROVER_B200_PIN", "background").strip().lower()
+
+    def attach(self, shm: SharedMemory, lo: int = 0, hi: Optional[int] = None):
+        """Prepare the bytes [lo, hi) of the segment (default: all of it) as this
+        process's DMA target: NUMA placement now (pages are faulted in by whoever
+        writes them first), pinning inline for small windows, else in the background
+        after the first transfer (pin_in_background)."""
+        hi = shm.size if hi is None else hi
+        window = (shm.address + lo, hi - lo)
+        if window == self._attached:
             return
         self.detach()
-        t0 = time.time()
-        self.ctx.host_register(addr, shm.size, prefault_threads=_host_threads())
-        self.register_seconds = time.time() - t0
-        self._registered_addr = addr
-        logger.info(
-            f"Pinned the {shm.size / 2**30:.2f} GiB checkpoint segment for DMA "
-            f"in {self.register_seconds:.2f}s.")
+        self._attached = window
+        addr, size = window
+        if size <= 0:
+            return
+        self.ctx.host_bind_numa(addr, size, _numa_remote_share(self.device_index))
+        if self._pin_mode() == "sync" or (size <= self.SYNC_PIN_MAX and self._pin_mode() != "none"):
+            t0 = time.time()
+            self.ctx.host_register(addr, size, prefault_threads=_host_threads())
+            self.register_seconds = time.time() - t0
+            self._pin_started = True
+            logger.info(f"Pinned the {size / 2**30:.2f} GiB checkpoint segment for DMA "
+                        f"in {self.register_seconds:.2f}s.")
+
+    def pin_in_background(self):
+        """Start pinning the window on a library thread (no-op when done/started)."""
+        if self._attached is None or self._pin_started or self._pin_mode() == "none":
+            return
+        addr, size = self._attached
+        if size <= 0:
+            return
+        self.ctx.host_register_background(addr, size)
+        self._pin_started = True
+
+    def pinned(self) -> bool:
+        return bool(self._attached) and self._pin_started and self.ctx.host_ready(self._attached[0])
 
     def detach(self):
-        if self._registered_addr:
+        if self._attached is not None and self._pin_started:
             try:
-                self.ctx.host_unregister(self._registered_addr)
+                self.ctx.host_unregister(self._attached[0])
             except native.NativeError as e:
                 logger.warning(f"host_unregister: {e}")
-            self._registered_addr = 0
+        self._attached = None
+        self._pin_started = False
 
-    def plan_for(self, ranges: List[Tuple[torch.Tensor, int, int]], keepalive: list,
-                 role: str = "save", stream=None):
-        """ranges: (tensor, segment offset, nbytes) per device-resident leaf.
-        One plan object per role ("save" / "restore"); when the tensors moved
-        (FSDP hands out fresh ones on every state_dict()) the plan is
-        re-targeted in place with a stream-ordered table upload."""
-        if not all(t.is_contiguous() for t, _, _ in ranges):
-            # rare (state_dict tensors are contiguous); device-side repack,
-            # kept alive until the pack kernel has consumed it
-            packed = []
-            for t, off, nbytes in ranges:
-                if not t.is_contiguous():
-                    t = t.detach().contiguous()
-                    keepalive.append(t)
-                packed.append((t, off, nbytes))
-            ranges = packed
-        ptrs = [t.data_ptr() for t, _, _ in ranges]
-        offs = [r[1] for r in ranges]
-        lens = [r[2] for r in ranges]
+    @staticmethod
+    def prepare_ranges(ranges: List[Tuple[torch.Tensor, int, int]], keepalive: list,
+                       for_write: bool = False):
+        """(tensor, segment offset, nbytes) -> parallel lists (ptrs, offsets, lengths).
+        Dense tensors are one range; row-strided ones one range per dense row;
+        anything else is repacked on the device first (save only — the copy lives in
+        `keepalive` until the gather kernel has consumed it)."""
+        ptrs, offs, lens = [], [], []
+        for t, off, nbytes in ranges:
+            if t.is_contiguous():
+                ptrs.append(t.data_ptr())
+                offs.append(off)
+                lens.append(nbytes)
+                continue
+            rows = _row_ranges(t, off)
+            if rows is None:
+                if for_write:
+                    raise ValueError("restore needs dense or row-strided CUDA targets "
+                                     f"(got shape {tuple(t.shape)}, strides {t.stride()})")
+                t = t.detach().contiguous()
+                keepalive.append(t)
+                ptrs.append(t.data_ptr())
+                offs.append(off)
+                lens.append(nbytes)
+                continue
+            for p, o, n in rows:
+                ptrs.append(p)
+                offs.append(o)
+                lens.append(n)
+        return ptrs, offs, lens
+
+    def plan_for(self, prepared, role: str = "save", stream=None, base: int = 0):
+        """prepared: (ptrs, segment offsets, lengths) from prepare_ranges.  `base` is
+        subtracted from the offsets (a window of the segment staged on its own: arena
+        byte 0 = segment byte `base`, the host base moves by the same amount).
+        One plan object per role ("save" / "restore"); when the tensors moved (FSDP
+        hands out fresh ones on every state_dict()) the plan is re-targeted in place
+        with a stream-ordered table upload."""
+        ptrs, offs, lens = prepared
+        if base:
+            offs = [o - base for o in offs]
         key = (ptrs, offs, lens)
         plan = self._plans.get(role)
         if plan is not None and plan.key == key:
@@ -388,6 +531,7 @@ class SharedMemoryHandler:
         self.metadata = SharedDict(name=CheckpointSharedObjPrefix.META_NAME + str(local_rank),
                                    create=host)
         self._need_creation = True
+        self._announced_once = False
         self._layout: Optional[_Layout] = None  # of the previous save (TensorMeta reuse)
         self._stager: Optional[_DeviceStager] = None
         self._pending: Optional[PendingSave] = None
@@ -438,6 +582,24 @@ class SharedMemoryHandler:
     def init_shared_memory(self, create=False, size=0):
         self.shared_memory = _create_shared_memory(self._shm_name, create=create, size=size)
         self._need_creation = False
+
+    def refresh_mapping(self):
+        """(Re-)attach when this process has no mapping yet or its mapping is stale: the
+        writer re-creates the segment when the payload size changes (optimizer state
+        filling in after the first save, DCP byte items whose pickled size drifts), and
+        a reader that kept the old mapping would persist old bytes under the new meta.
+        Call with the shard lock held / after the meta said writing_shm=False."""
+        shm = self.shared_memory
+        if shm is not None and not self._need_creation and not shm.stale():
+            return
+        if self._pending is not None:
+            return  # the writer side never refreshes under its own drain
+        if shm is not None:
+            if self._stager is not None:
+                self._stager.detach()
+            shm.close()
+            self.shared_memory = None
+        self.init_shared_memory(create=False)
 
     def _create_tensor_meta(self, value):
         """Meta of one leaf at the current end of the layout (API parity with
@@ -508,7 +670,8 @@ class SharedMemoryHandler:
                      keepalive: Optional[list] = None,
                      pre_drain: Optional[Callable[[], None]] = None,
                      on_error: Optional[Callable[[], None]] = None,
-                     in_place: Optional[bool] = None):
+                     in_place: Optional[bool] = None,
+                     window: Optional[Tuple[int, int]] = None):
         """Move bytes into the (already sized) segment.
 
         device_ranges / host_ranges: (tensor, segment offset, nbytes) for CUDA /
@@ -520,6 +683,12 @@ class SharedMemoryHandler:
         tensors themselves, so they must not be written until the save is done
         (wait_pending / PendingSave.wait).  Also chosen, together with blocking,
         when HBM has no room for the snapshot arena.
+        window=(lo, hi): this process is responsible for the segment bytes [lo, hi)
+        only (cooperative save of a replicated state: every local rank drains its own
+        slice of the same image over its own PCIe link): CUDA ranges are clipped to
+        the window, the arena holds hi-lo bytes, only that part of the segment is
+        pinned.  Host ranges / raw chunks are written as given (the caller hands them
+        to one rank only).
         """
         keepalive = keepalive if keepalive is not None else []
         for chunk, off in raw_chunks:
@@ -538,9 +707,21 @@ class SharedMemoryHandler:
             native.host_pack(self.shared_memory.address, ptrs, offs, lens, _host_threads())
             del keep
         ctx, ticket = None, 0
+        stager = None
+        prepared = None
         if device_ranges:
             stager = self._stager_for([r[0] for r in device_ranges])
-            stager.attach(self.shared_memory)
+            # a dense repack of an oddly strided leaf runs on the CURRENT stream: do it
+            # before a side stream is made to wait for that stream
+            prepared = stager.prepare_ranges(device_ranges, keepalive)
+            if window is not None:
+                prepared = _clip_ranges(prepared, window[0], window[1])
+                if not prepared[0]:
+                    prepared = None
+        if prepared is not None:
+            lo, hi = window if window is not None else (0, self.shared_memory.size)
+            stager.attach(self.shared_memory, lo, hi)
+            host_addr = self.shared_memory.address + lo
             current = torch.cuda.current_stream(stager.device_index)
             if stream is None:
                 stream = current
@@ -549,13 +730,13 @@ class SharedMemoryHandler:
                 # stream has enqueued so far, and the caller must make the training
                 # stream wait for `last_pack_event` before it MUTATES the tensors
                 stream.wait_stream(current)
-            plan = stager.plan_for(device_ranges, keepalive, role="save", stream=stream)
+            plan = stager.plan_for(prepared, role="save", stream=stream, base=lo)
             in_place = self.in_place if in_place is None else in_place
-            cut = None  # hybrid: segment offset from which the tensors are snapshotted
+            cut = None  # hybrid: window offset from which the tensors are snapshotted
             if in_place:
                 arena = stager.ARENA_NONE
-                cut = self._hybrid_cut(stager, plan, device_ranges)
-                if cut is not None and cut <= min(r[1] for r in device_ranges) \
+                cut = self._hybrid_cut(stager, plan, prepared[1], lo)
+                if cut is not None and cut <= min(prepared[1]) - lo \
                         and stager.ensure_arena(plan) == stager.ARENA_FULL:
                     in_place, cut, arena = False, None, stager.ARENA_FULL  # everything fits
             else:
@@ -565,18 +746,21 @@ class SharedMemoryHandler:
                 in_place = blocking = True
             # bounded-arena saves drain inside save_async: announce first, inline
             windowed = arena == stager.ARENA_WINDOWED
+            if windowed and not stager.pinned():
+                stager.ctx.host_register(*stager._attached, prefault_threads=_host_threads())
+                stager._pin_started = True
             hold = pre_drain is not None and not blocking and not windowed
             if pre_drain is not None and not hold:
                 pre_drain()
                 pre_drain = None
             if in_place and cut is not None:
-                ticket = plan.save_hybrid_async(self.shared_memory.address, cut, stream, hold=hold)
+                ticket = plan.save_hybrid_async(host_addr, cut, stream, hold=hold)
             elif in_place:
-                ticket = plan.save_direct_async(self.shared_memory.address, stream, hold=hold)
+                ticket = plan.save_direct_async(host_addr, stream, hold=hold)
             else:
-                ticket = plan.save_async(self.shared_memory.address, stream, hold=hold)
+                ticket = plan.save_async(host_addr, stream, hold=hold)
             self._last_ticket = (stager.ctx, ticket)
-            self.last_hybrid_cut = cut
+            self.last_hybrid_cut = None if cut is None else cut + lo
             self.last_save_in_place = in_place
             if in_place:
                 self.last_pack_event = None  # there is no snapshot to wait for, only the drain
@@ -588,7 +772,16 @@ class SharedMemoryHandler:
         if ctx is None and pre_drain is not None:
             pre_drain()
             pre_drain = None
-        pending = PendingSave(ctx, ticket, finish or (lambda: None), keepalive,
+        user_finish = finish or (lambda: None)
+        if ctx is not None:
+            def finish_and_pin():
+                user_finish()
+                # the first transfer of a large window went through bounce slots; pin the
+                # window now, off every critical path, so the next ones are plain DMA
+                stager.pin_in_background()
+        else:
+            finish_and_pin = user_finish
+        pending = PendingSave(ctx, ticket, finish_and_pin, keepalive,
                               pre_drain=pre_drain if ctx is not None else None,
                               on_error=on_error)
         self._pending = pending
@@ -604,9 +797,9 @@ class SharedMemoryHandler:
 
     MIN_SNAPSHOT_BYTES = 64 << 20  # below this a snapshot part is not worth a kernel
 
-    def _hybrid_cut(self, stager: _DeviceStager, plan, device_ranges) -> Optional[int]:
-        """In-place save with a snapshot budget: the segment offset from which the
-        tensors fit into the arena (None: no budget / no arena -> pure in-place)."""
+    def _hybrid_cut(self, stager: _DeviceStager, plan, offsets, base: int = 0) -> Optional[int]:
+        """In-place save with a snapshot budget: the (window-relative) offset from which
+        the tensors fit into the arena (None: no budget / no arena -> pure in-place)."""
         budget = self.in_place_snapshot_bytes
         if budget <= 0:
             return None
@@ -626,8 +819,9 @@ class SharedMemoryHandler:
                     break
         cap = min(stager.ctx.arena_info()[1], budget)
         end, cut = plan.arena_end, None
-        for _, off, _ in sorted(device_ranges, key=lambda r: r[1], reverse=True):
-            if end - off > cap:
+        for off in sorted((o - base for o in offsets), reverse=True):
+            # the arena's byte 0 stands for the cut rounded down to 128 B
+            if end - (off & ~127) > cap:
                 break
             cut = off
         return cut
@@ -680,9 +874,14 @@ class SharedMemoryHandler:
         # nothing touches the segment before the drain: the announcement (a
         # pickle + two socket round trips) moves to the completion thread and
         # the drain is held until it is out.
-        defer_announce = (not blocking) and bool(lay.device_leaves) and not lay.host_leaves
+        # The very first announcement of a handler is made inline: until it is out the
+        # agent's dict holds no step at all, and a SAVE event that overtakes it would
+        # find "no shard has a step" (ckpt_saver._check_shard_step_consistence).
+        defer_announce = ((not blocking) and bool(lay.device_leaves) and not lay.host_leaves
+                          and self._announced_once)
         if not defer_announce:
             announce()
+        self._announced_once = True
 
         def finish():
             conf.writing_shm = False
@@ -717,8 +916,7 @@ class SharedMemoryHandler:
         config = meta_dict.get(DLROVER_CKPT_CONFIG_KEY, CheckpointConfig())
         if not meta_dict or config.writing_shm:
             return {}
-        if self.shared_memory is None or self._need_creation:
-            self.init_shared_memory(create=False)
+        self.refresh_mapping()
         if not self.shared_memory:
             return {}
         report_local_event(EventReportConstants.TYPE_INFO, str(config.rank),
@@ -745,8 +943,7 @@ class SharedMemoryHandler:
         config = meta_dict.get(DLROVER_CKPT_CONFIG_KEY, CheckpointConfig())
         if not meta_dict or config.writing_shm:
             raise RuntimeError("no consistent in-memory checkpoint to restore from")
-        if self.shared_memory is None or self._need_creation:
-            self.init_shared_memory(create=False)
+        self.refresh_mapping()
         if not self.shared_memory:
             raise RuntimeError("the checkpoint segment does not exist")
 
@@ -797,16 +994,14 @@ class SharedMemoryHandler:
                                    [m.numel * m.element_size for _, m in dense], _host_threads())
             stats["host_bytes"] = float(sum(m.numel * m.element_size for _, m in host_pairs))
             if device_pairs:
-                for t, _ in device_pairs:
-                    if not t.is_contiguous():
-                        raise ValueError("restore_into needs contiguous CUDA targets")
                 stager = self._stager_for([t for t, _ in device_pairs])
+                prepared = stager.prepare_ranges(
+                    [(t, m.offset, m.numel * m.element_size) for t, m in device_pairs], [],
+                    for_write=True)
                 stager.attach(self.shared_memory)
                 if stream is None:
                     stream = torch.cuda.current_stream(stager.device_index)
-                plan = stager.plan_for(
-                    [(t, m.offset, m.numel * m.element_size) for t, m in device_pairs], [],
-                    role="restore", stream=stream)
+                plan = stager.plan_for(prepared, role="restore", stream=stream)
                 stats.update(self._run_restore(stager, plan, stream))
         return stats
 
@@ -822,11 +1017,16 @@ class SharedMemoryHandler:
             direct = forced == "direct"
         if not direct and stager.ensure_arena(plan) == stager.ARENA_NONE:
             direct = True
+        staged = not stager.pinned()  # e.g. a restarted trainer: bounce slots, no 16 GB pin
+        t0 = time.perf_counter()
         plan.restore_async(self.shared_memory.address, stream, direct=direct)
         stager.ctx.restore_wait()
+        wall_ms = (time.perf_counter() - t0) * 1e3
         fill, scatter, _ = stager.ctx.restore_timings()
         self.last_restore_stats = {"device_bytes": float(plan.payload_bytes), "fill_ms": fill,
-                                   "scatter_ms": scatter, "direct": float(direct)}
+                                   "scatter_ms": scatter, "direct": float(direct),
+                                   "staged": float(staged), "wall_ms": wall_ms}
+        stager.pin_in_background()  # the next save wants plain DMA
         return dict(self.last_restore_stats)
 
     def read_ranges(self, device_ranges, stream=None) -> Dict[str, float]:
@@ -836,20 +1036,20 @@ class SharedMemoryHandler:
         self.wait_pending()
         if not device_ranges:
             return {"device_bytes": 0.0, "fill_ms": 0.0, "scatter_ms": 0.0}
-        if self.shared_memory is None or self._need_creation:
-            self.init_shared_memory(create=False)
+        self.refresh_mapping()
         if not self.shared_memory:
             raise RuntimeError("the checkpoint segment does not exist")
         for t, off, nbytes in device_ranges:
-            if not (t.is_cuda and t.is_contiguous()):
-                raise ValueError("read_ranges needs contiguous CUDA targets")
+            if not t.is_cuda:
+                raise ValueError("read_ranges needs CUDA targets")
             if off + nbytes > self.shared_memory.size or t.numel() * t.element_size() != nbytes:
                 raise ValueError("read_ranges: range does not fit the segment / the tensor")
         stager = self._stager_for([r[0] for r in device_ranges])
+        prepared = stager.prepare_ranges(device_ranges, [], for_write=True)
         stager.attach(self.shared_memory)
         if stream is None:
             stream = torch.cuda.current_stream(stager.device_index)
-        plan = stager.plan_for(device_ranges, [], role="restore", stream=stream)
+        plan = stager.plan_for(prepared, role="restore", stream=stream)
         return self._run_restore(stager, plan, stream)
 
     # -- queries ------------------------------------------------------------------------

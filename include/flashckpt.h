@@ -39,7 +39,7 @@
 extern "C" {
 #endif
 
-#define FC_VERSION 100 /* 0.1.0 */
+#define FC_VERSION 200 /* 0.2.0 */
 
 enum {
   FC_OK = 0,
@@ -91,6 +91,31 @@ int fc_set_arena_limit(fc_ctx* ctx, uint64_t bytes);
  * copy_ loop).  Registration is per process; the agent never needs it. */
 int fc_host_register(fc_ctx* ctx, void* host, uint64_t bytes, int prefault_threads);
 int fc_host_unregister(fc_ctx* ctx, void* host);
+/* The same pinning, off the caller's thread: a library thread registers the range
+ * slice by slice (slice_bytes, 0 = 64 MiB; no DMA of this library ever straddles two
+ * slices) and the call returns at once.  Until fc_host_ready() answers FC_OK, saves
+ * and restores that touch the range go through the staged path below — so neither the
+ * first save of a run nor the restore of a restarted trainer waits 3-6 s for
+ * cudaHostRegister of a 16 GB segment (the reference never pins: every one of its
+ * copies is a pageable cudaMemcpy, ckpt_saver.py:221-231, :144-161).
+ * fc_host_ready: FC_OK pinned, FC_ENOTREADY in progress, < 0 failed / unknown range. */
+int fc_host_register_background(fc_ctx* ctx, void* host, uint64_t bytes, uint64_t slice_bytes);
+int fc_host_ready(fc_ctx* ctx, const void* host);
+/* NUMA placement of a range that has not been touched yet (the pages of the segment
+ * are faulted in by whoever writes them first): prefer the node of the context's GPU;
+ * remote_per256 > 0 on a two-socket host binds that many of every 256 consecutive
+ * 2-MiB blocks to the OTHER socket instead (when more GPUs of one socket drain at once
+ * than its memory absorbs and the other socket is idle).  fc_host_register applies the
+ * all-local policy by itself.  Best effort. */
+int fc_host_bind_numa(fc_ctx* ctx, void* host, uint64_t bytes, int remote_per256);
+/* NUMA node of a CUDA device (-1 unknown) and the number of nodes of the host. */
+int fc_device_numa_node(int device, int* node, int* n_nodes);
+/* Staged path for host ranges that are not (completely) registered: `threads` host
+ * threads (default 8), each with its own stream and two pinned bounce slots of
+ * slot_bytes (default 8 MiB), memcpy between segment and slot while the DMA of their
+ * other slot is in flight.  Chosen automatically by fc_save_* / fc_restore_*; a
+ * staged restore returns when the data is on the device.  0 keeps a value. */
+int fc_set_stage(fc_ctx* ctx, int threads, uint64_t slot_bytes);
 
 /* ---- plan: the on-device "serialisation header" -------------------------- */
 
@@ -178,8 +203,10 @@ int fc_save_cancel(fc_ctx* ctx, uint64_t ticket);
 int fc_save_direct_async(fc_plan* plan, void* host_base, void* compute_stream, int hold,
                          uint64_t* ticket);
 /* Hybrid of the two: tensors whose segment offset is >= `cut` (a tensor boundary)
- * are snapshotted into the arena (which must hold arena_end - cut bytes; its byte 0
- * stands for offset `cut`), the tensors below `cut` are drained in place — first, so
+ * are snapshotted into the arena (which must hold arena_end - (cut & ~127) bytes; its
+ * byte 0 stands for offset `cut` rounded down to 128 B, so every range keeps its
+ * alignment class and goes through the same bulk / shift kernels as a full save),
+ * the tensors below `cut` are drained in place — first, so
  * that they are released as early as possible.  Spends whatever HBM is to spare on
  * shortening the time the sources stay frozen: (bytes below cut) / PCIe rate.
  * (The reference keeps the sources frozen for the whole copy, ckpt_saver.py:198-231.) */
@@ -206,6 +233,16 @@ int fc_save_timings(fc_ctx* ctx, uint64_t ticket, float* pack_ms, float* drain_m
  * k+1 only after piece k completed (default: depth 1 x 32 MiB; a foreign copy
  * then waits at most one piece, ~0.6 ms).  0 keeps the current value. */
 int fc_set_drain(fc_ctx* ctx, uint64_t piece_bytes, int depth);
+/* How the pump keeps "one piece in flight":
+ *   FC_DRAIN_HOST_PACED  the host submits piece k+1 after piece k completed (one host
+ *                        round trip between two pieces; a spinning wait hides most of it);
+ *   FC_DRAIN_PINGPONG    pieces alternate between two copy streams, piece k waiting on
+ *                        the DEVICE for piece k-1: no stream ever has a second copy
+ *                        queued, no host round trip between pieces, the host thread
+ *                        sleeps in a blocking wait.  Small pieces then cost no
+ *                        throughput (profiles/r02_drain_modes.md). */
+enum { FC_DRAIN_HOST_PACED = 0, FC_DRAIN_PINGPONG = 1 };
+int fc_set_drain_mode(fc_ctx* ctx, int mode);
 
 /* ---- host-resident leaves --------------------------------------------------- */
 

@@ -253,3 +253,32 @@ def test_shared_memory_not_tracked_by_resource_tracker(run_env):
     assert bytes(s.buf[0:2]) == b"ok"
     s.unlink()
     s.close()
+
+
+def test_forced_release_invalidates_the_old_holders_claim():
+    """AsyncCheckpointSaver.release_locks() frees a lock on the owner side; the client
+    that held it must not be able to drop the lock someone else has taken since."""
+    import uuid
+
+    from dlrover_b200.common.multi_process import SharedLock
+
+    name = "epoch" + uuid.uuid4().hex[:6]
+    owner = SharedLock(name=name, create=True)
+    a = SharedLock(name=name, create=False)
+    b = SharedLock(name=name, create=False)
+    try:
+        assert a.acquire(blocking=False)
+        owner.release()                      # forced by the owner
+        assert b.acquire(blocking=False)     # someone else takes it
+        a.release()                          # stale claim: must be ignored
+        assert owner.locked()
+        a.close()                            # ... also on disconnect
+        import time
+        time.sleep(0.2)
+        assert owner.locked()
+        b.release()
+        assert not owner.locked()
+    finally:
+        b.close()
+        owner.unlink()
+        owner.close()

@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_version_and_strerror():
     lib = native.load_library()
-    assert lib.fc_version() == 100
+    assert lib.fc_version() == 200
     assert lib.fc_strerror(0) == b"ok"
     assert b"flight" in lib.fc_strerror(native.FC_EBUSY)
 
