@@ -381,8 +381,11 @@ def run_ours(args):
         ckpt.wait_memory_save()
 
     t0 = time.perf_counter()
-    api_step(1)  # creates + pins this rank's segment, builds the plan
+    api_step(1)  # creates the segment (first touch through bounce slots), builds the plan
     first_save_s = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    pinned = ckpt.engine.wait_segment_pinned(120)  # background pin: steady state from here
+    background_pin_s = time.perf_counter() - t0
     for i in range(max(args.warmup, 3)):
         api_step(2 + i)
     barrier_sync(world)
@@ -432,6 +435,7 @@ def run_ours(args):
                     "h2d_bytes_per_step": 0, "d2h_bytes_per_step": S,
                     "api": "DdpCheckpointer.save_checkpoint(MEMORY)+wait_memory_save",
                     "first_save_s": first_save_s,
+                    "background_pin_s": background_pin_s, "pinned": bool(pinned),
                     "note": "inputs of this path are the live device-resident parameters; "
                             "the host buffer is the shm segment the drain fills"},
             "stall_ms": stall,

@@ -756,13 +756,28 @@ static fc_ctx::HostReg* reg_covering(fc_ctx* c, const uint8_t* p, uint64_t len) 
   return nullptr;
 }
 
-// 0 when [p, p+len) lies in a completely registered range (plain DMA), else the
-// number of host threads the staged path should use.
+static bool is_pinned_host(const void* q) {
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, q) != cudaSuccess) {
+    (void)cudaGetLastError();
+    return false;
+  }
+  return at.type == cudaMemoryTypeHost;
+}
+
+// 0 when [p, p+len) is page-locked for CUDA (a completed fc_host_register*, or memory
+// the caller pinned itself, e.g. cudaHostAlloc): plain DMA.  Else the number of host
+// threads the staged path should use.
 static int staged_threads_for(fc_ctx* c, const uint8_t* p, uint64_t len) {
   if (len == 0 || getenv("FC_NO_STAGING")) return 0;
-  std::lock_guard<std::mutex> lk(c->mu);
-  fc_ctx::HostReg* r = reg_covering(c, p, len);
-  if (r && r->state == 1) return 0;
+  {
+    std::lock_guard<std::mutex> lk(c->mu);
+    for (auto& r : c->regs) {
+      const bool overlaps = p < r->base + r->bytes && r->base < p + len;
+      if (overlaps && r->state != 1) return std::max(1, c->stage_threads);  // still pinning
+    }
+  }
+  if (is_pinned_host(p) && is_pinned_host(p + len - 1)) return 0;
   return std::max(1, c->stage_threads);
 }
 

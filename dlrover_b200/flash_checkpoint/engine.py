@@ -501,6 +501,11 @@ class CheckpointEngine(metaclass=ABCMeta):
         """Block until the drain of the last save has landed in shared memory."""
         return self._shm_handler.wait_pending(timeout)
 
+    def wait_segment_pinned(self, timeout: float = 120.0) -> bool:
+        """Block until the background pinning of this rank's part of the segment is done
+        (never required; the first transfers simply go through bounce slots)."""
+        return self._shm_handler.wait_segment_pinned(timeout)
+
     def last_save_timings(self):
         """(pack_ms, drain_ms, total_ms) device times of the last finished save."""
         return self._shm_handler.last_timings

@@ -348,6 +348,14 @@ class _DeviceStager:
     def pinned(self) -> bool:
         return bool(self._attached) and self._pin_started and self.ctx.host_ready(self._attached[0])
 
+    def wait_pinned(self, timeout: float = 120.0) -> bool:
+        deadline = time.time() + timeout
+        while not self.pinned():
+            if not self._pin_started or time.time() > deadline:
+                return False
+            time.sleep(0.01)
+        return True
+
     def detach(self):
         if self._attached is not None and self._pin_started:
             try:
@@ -617,6 +625,14 @@ class SharedMemoryHandler:
             self.wait_pending(timeout=120)
         except BaseException:
             pass
+
+    def wait_segment_pinned(self, timeout: float = 120.0) -> bool:
+        """True once this process's window of the segment is page-locked (transfers are
+        plain DMA from then on).  Large windows are pinned by a library thread after the
+        first save / restore; nothing has to wait for it — benchmarks do, to time the
+        steady state."""
+        self.wait_pending()
+        return self._stager is not None and self._stager.wait_pinned(timeout)
 
     # -- pending drain ----------------------------------------------------------------
     def pending_save(self) -> Optional[PendingSave]:

@@ -185,7 +185,14 @@ def test_ddp_checkpointer(agent, tmp_path):
     steps = sorted(int(d) for d in os.listdir(tmp_path) if d.isdigit())
     assert steps == [30, 40]  # KeepLatestStepStrategy(2)
     assert sorted(os.listdir(tmp_path / "40")) == ["rank_0.pt"]
-    assert ckpt.load_checkpoint_into(model.state_dict(), strict=False) == 0 or True
+    # memory still holds step 40: scatter it back into the (zeroed) live model
+    want = {k: v.clone() for k, v in sd["model"].items()}
+    with torch.no_grad():
+        for p in model.parameters():
+            p.zero_()
+    live = {"model": model.state_dict(), "optimizer": sd["optimizer"], "step": 0}
+    assert ckpt.load_checkpoint_into(live, strict=False) == 40
+    assert all(torch.equal(model.state_dict()[k], v) for k, v in want.items())
     ckpt.engine.close()
 
 

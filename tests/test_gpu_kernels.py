@@ -313,8 +313,9 @@ def test_in_place_save_and_restore(cuda_device):
 
 
 def test_hybrid_save_snapshot_tail_in_place_head(cuda_device):
-    """fc_save_hybrid_async: tensors at offsets >= cut go through the arena (LSU gather
-    over a table slice, arena byte 0 = offset cut), the rest is drained in place first;
+    """fc_save_hybrid_async: tensors at offsets >= cut go through the arena (the slices of
+    the bulk / shift / resid tables from the cut on, arena byte 0 = the cut rounded down to
+    128 B), the rest is drained in place first;
     fc_save_pack_done / fc_save_sources_wait tell when the tensors may change."""
     ctx = native.get_context(0)
     g = torch.Generator().manual_seed(31)
@@ -331,7 +332,7 @@ def test_hybrid_save_snapshot_tail_in_place_head(cuda_device):
     stream = torch.cuda.current_stream()
     for first_snapshotted in (0, 4, 7, len(leaves)):   # all snapshot ... all in place
         cut = offsets[first_snapshotted] if first_snapshotted < len(leaves) else total
-        ctx.arena_reserve(max(total - cut, 8))
+        ctx.arena_reserve(max(total - (cut & ~127), 8))
         host.zero_()
         k0, m0 = ctx.launch_count()
         ticket = plan.save_hybrid_async(host.data_ptr(), cut, stream, hold=True)
@@ -349,7 +350,10 @@ def test_hybrid_save_snapshot_tail_in_place_head(cuda_device):
             t.add_(1)
         ctx.save_wait(ticket)
         k1, m1 = ctx.launch_count()
-        assert k1 - k0 == (1 if first_snapshotted < len(leaves) else 0)
+        if first_snapshotted < len(leaves):
+            assert 1 <= k1 - k0 <= 3   # bulk / shift / resid slices of the tables
+        else:
+            assert k1 == k0
         assert np.array_equal(host.numpy(), want), first_snapshotted
         for t, k in zip(leaves, keep):
             t.copy_(k)

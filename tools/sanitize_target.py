@@ -38,8 +38,8 @@ for variant in (native.VARIANT_TMA, native.VARIANT_LSU):
     ctx.restore_wait()
     for a, b in zip(tensors, keep):
         assert torch.equal(a, b)
-# hybrid / in-place saves: LSU gather over a table slice into an arena whose byte 0
-# stands for the cut offset; in-place restore
+# hybrid / in-place saves: the bulk / shift / resid table slices from the cut on, into an
+# arena whose byte 0 stands for the cut rounded down to 128 B; in-place restore
 ctx.set_variant(native.VARIANT_AUTO)
 for first in (0, 3, 6, len(tensors)):
     cut = offs[first] if first < len(tensors) else o
@@ -57,4 +57,24 @@ plan.restore_async(host.data_ptr(), torch.cuda.current_stream(), direct=True)
 ctx.restore_wait()
 for a, b in zip(tensors, keep):
     assert torch.equal(a, b)
+# staged path (host range nobody pinned) and the ping-pong drain
+pageable = np.zeros(o, dtype=np.uint8)
+ctx.set_stage(3, 256 << 10)
+tk = plan.save_async(pageable.ctypes.data, torch.cuda.current_stream())
+ctx.save_wait(tk)
+for t, off in zip(tensors, offs):
+    assert np.array_equal(pageable[off:off + t.numel()], t.cpu().numpy())
+for t in tensors:
+    t.zero_()
+plan.restore_async(pageable.ctypes.data, torch.cuda.current_stream())
+ctx.restore_wait()
+for a, b in zip(tensors, keep):
+    assert torch.equal(a, b)
+ctx.set_drain_mode(native.DRAIN_PINGPONG)
+ctx.set_drain(128 << 10, 1)
+host.zero_()
+tk = plan.save_async(host.data_ptr(), torch.cuda.current_stream())
+ctx.save_wait(tk)
+for t, off in zip(tensors, offs):
+    assert np.array_equal(host.numpy()[off:off + t.numel()], t.cpu().numpy())
 print("SANITIZE_TARGET_OK")
