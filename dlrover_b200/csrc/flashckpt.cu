@@ -174,6 +174,26 @@ struct fc_ctx {
 
 static fc_ctx::HostReg* reg_covering(fc_ctx* c, const uint8_t* p, uint64_t len);
 
+// A host range pinned slice by slice is a row of separate registrations to CUDA, and
+// a cudaMemcpy that straddles two of them fails with "invalid argument": every DMA
+// the library issues is cut at the slice boundaries of the range it touches.
+struct SliceClip {
+  const uint8_t* base = nullptr;
+  uint64_t slice = 0;
+  SliceClip(fc_ctx* c, const uint8_t* some_byte) {
+    std::lock_guard<std::mutex> lk(c->mu);
+    if (fc_ctx::HostReg* r = reg_covering(c, some_byte, 1)) {
+      base = r->base;
+      slice = r->slice;
+    }
+  }
+  uint64_t operator()(const uint8_t* p, uint64_t len) const {
+    if (!slice) return len;
+    const uint64_t in = (uint64_t)(p - base) % slice;
+    return std::min<uint64_t>(len, slice - in);
+  }
+};
+
 // ---- staged transfers ---------------------------------------------------------
 // A host range that is not (yet) cudaHostRegister-ed — the segment a restarted
 // trainer has just attached to, or a brand-new one whose registration (3-6 s for
@@ -323,21 +343,9 @@ static void pump_main(fc_ctx* c) {
       job.direct = false;
     }
     // a range registered slice by slice: no DMA may straddle two slices
-    uint8_t* reg_base = nullptr;
-    uint64_t reg_slice = 0;
-    if (!job.runs.empty() || !job.spans.empty()) {
-      std::lock_guard<std::mutex> lk(c->mu);
-      const uint64_t first = !job.runs.empty() ? job.runs.front().off : job.spans.front().off;
-      if (fc_ctx::HostReg* r = reg_covering(c, job.host + first, 1)) {
-        reg_base = r->base;
-        reg_slice = r->slice;
-      }
-    }
-    auto clip = [&](const uint8_t* dst, uint64_t len) {
-      if (!reg_slice) return len;
-      const uint64_t in = (uint64_t)(dst - reg_base) % reg_slice;
-      return std::min<uint64_t>(len, reg_slice - in);
-    };
+    const uint64_t first_off = !job.runs.empty() ? job.runs.front().off
+                               : !job.spans.empty() ? job.spans.front().off : 0;
+    const SliceClip clip(c, job.host + first_off);
     if (job.direct) {
       // one batch (<= drain_piece bytes, <= 64 copies) in flight, then wait: same
       // pacing rule as below, small tensors share a batch
@@ -795,8 +803,14 @@ static void register_slices(fc_ctx* c, fc_ctx::HostReg* r) {
       r->state = -1;
       return;
     }
-    std::lock_guard<std::mutex> lk(c->mu);
-    r->done.push_back(r->base + o);
+    {
+      std::lock_guard<std::mutex> lk(c->mu);
+      r->done.push_back(r->base + o);
+    }
+    // cudaHostRegister holds a driver lock every other CUDA call of the process needs
+    // (measured: a kernel launch issued during a 16 GB registration waits for all of
+    // it, 0.87 s): give the training thread a window after every slice
+    usleep(500);
   }
   if (!r->cancel) r->state = 1;
 }
@@ -853,7 +867,7 @@ extern "C" int fc_host_register_background(fc_ctx* c, void* host, uint64_t bytes
     return fail(FC_EINVAL, "fc_host_register_background: bad argument%s%s");
   if (find_reg(c, host)) return FC_OK;  // known: in progress or done
   const uint64_t pg = (uint64_t)sysconf(_SC_PAGESIZE);
-  if (slice_bytes == 0) slice_bytes = 64ull << 20;
+  if (slice_bytes == 0) slice_bytes = 256ull << 20;
   slice_bytes = std::max<uint64_t>((slice_bytes + pg - 1) / pg * pg, 2ull << 20);
   std::unique_ptr<fc_ctx::HostReg> r(new fc_ctx::HostReg());
   r->base = static_cast<uint8_t*>(host);
@@ -1315,10 +1329,11 @@ static std::vector<Window> make_windows(const fc_plan* p, uint64_t arena_bytes) 
 template <bool TO_HOST>
 static int copy_window(fc_ctx* c, const fc_plan* p, uint8_t* host, uint64_t lo, uint64_t hi,
                        uint64_t base) {
+  const SliceClip clip(c, host + lo);
   for (const FcRun& r : p->runs) {
     uint64_t a = std::max(lo, r.off), b = std::min(hi, r.off + r.len);
-    for (uint64_t o = a; o < b; o += c->drain_piece) {
-      const uint64_t len = std::min<uint64_t>(c->drain_piece, b - o);
+    for (uint64_t o = a, len = 0; o < b; o += len) {
+      len = clip(host + o, std::min<uint64_t>(c->drain_piece, b - o));
       if (TO_HOST)
         FC_CUDA(cudaMemcpyAsync(host + o, c->arena + (o - base), len, cudaMemcpyDeviceToHost,
                                 c->copy_stream));
@@ -1597,9 +1612,10 @@ extern "C" int fc_restore_direct_async(fc_plan* p, const void* host_base, void* 
     c->restore_inflight = true;
     return FC_OK;
   }
+  const SliceClip clip(c, p->spans.empty() ? hb : hb + p->spans.front().off);
   for (const FcSpan& sp : p->spans)
-    for (uint64_t o = 0; o < sp.len; o += kDmaPiece) {
-      uint64_t len = std::min<uint64_t>(kDmaPiece, sp.len - o);
+    for (uint64_t o = 0, len = 0; o < sp.len; o += len) {
+      len = clip(hb + sp.off + o, std::min<uint64_t>(kDmaPiece, sp.len - o));
       FC_CUDA(cudaMemcpyAsync((uint8_t*)(uintptr_t)sp.tptr + o, hb + sp.off + o, len,
                               cudaMemcpyHostToDevice, c->copy_stream));
       c->n_memcpys += 1;
@@ -1872,9 +1888,10 @@ extern "C" int fc_restore_async(fc_plan* p, const void* host_base, void* stream)
     c->restore_inflight = true;
     return FC_OK;
   }
+  const SliceClip clip(c, p->runs.empty() ? hb : hb + p->runs.front().off);
   for (const FcRun& r : p->runs)
-    for (uint64_t o = 0; o < r.len; o += kDmaPiece) {
-      uint64_t len = std::min<uint64_t>(kDmaPiece, r.len - o);
+    for (uint64_t o = 0, len = 0; o < r.len; o += len) {
+      len = clip(hb + r.off + o, std::min<uint64_t>(kDmaPiece, r.len - o));
       FC_CUDA(cudaMemcpyAsync(c->arena + r.off + o, hb + r.off + o, len, cudaMemcpyHostToDevice,
                               c->copy_stream));
       c->n_memcpys += 1;

@@ -50,6 +50,11 @@ class DdpCheckpointer(Checkpointer):
             None (keep everything).
         save_timeout: seconds agent rank 0 waits for all shards.
         replica_count: in-memory replicas on other nodes.
+        cooperative: replicated state (local_shard_num=1) on a node with several local
+            ranks: every local rank drains 1/n of the one image into the one segment
+            (n PCIe links instead of one).  None = on when possible
+            (DLROVER_B200_COOP_DRAIN=0 turns it off), False = the reference's policy
+            (only local rank 0 writes).
 
     Example::
         ckpt = DdpCheckpointer("/tmp/checkpoint/")
@@ -65,7 +70,7 @@ class DdpCheckpointer(Checkpointer):
     def __init__(self, checkpoint_dir: str, local_shard_num=1, global_shard_num=1,
                  comm_backend="", deletion_strategy=None,
                  save_timeout=CheckpointConstant.SAVE_TIMEOUT, replica_count=0,
-                 async_drain=None):
+                 async_drain=None, cooperative=None):
         self.checkpoint_dir = checkpoint_dir
         self._rank = dist.get_rank() if dist.is_initialized() else 0
         self.storage = get_checkpoint_storage(deletion_strategy)
@@ -78,6 +83,7 @@ class DdpCheckpointer(Checkpointer):
             save_timeout=save_timeout,
             replica_count=replica_count,
             async_drain=async_drain,
+            cooperative=cooperative,
         )
 
     def save_checkpoint(self, step, state_dict, path="", storage_type=StorageType.DISK):

@@ -36,6 +36,8 @@ from typing import Dict, List, Optional
 import torch
 import torch.distributed as dist
 
+from ..common.ctl_segment import ControlSegment
+from ..shm_handler import CoopContext
 from ..ckpt_saver import (
     DLROVER_CKPT_CONFIG_KEY,
     AsyncCheckpointSaver,
@@ -261,6 +263,9 @@ class CheckpointEngine(metaclass=ABCMeta):
     """
 
     saver_proc = None
+    # engines whose state is REPLICATED across the local ranks may save cooperatively
+    # (every local rank drains 1/n of the one image; see _cooperative_save)
+    _supports_cooperative = False
 
     def __init__(self, checkpoint_dir: str, storage: CheckpointStorage, comm_backend: str = "",
                  save_timeout: int = CheckpointConstant.SAVE_TIMEOUT, replica_count=0,
@@ -282,6 +287,9 @@ class CheckpointEngine(metaclass=ABCMeta):
         self._world_size = 1
         self._loader_group = None
         self._saver_group = None
+        self._coop_group = None
+        self._coop_wanted = False
+        self._coop_ctl: Optional[ControlSegment] = None
         self._saving_ranks: Optional[List[int]] = None
         self._init_sync_group(comm_backend)
 
@@ -315,6 +323,10 @@ class CheckpointEngine(metaclass=ABCMeta):
         if backend != default_backend:
             self._loader_group = dist.new_group(backend=backend, timeout=timedelta(seconds=60))
         self._saving_ranks = self.get_saving_ranks()
+        self._coop_wanted = self._cooperative_by_config()
+        if self._coop_wanted and backend != default_backend:
+            # the cooperative save's readiness check spans ALL ranks
+            self._coop_group = dist.new_group(backend=backend, timeout=timedelta(seconds=60))
         everyone_saves = self._saving_ranks is None or len(self._saving_ranks) == self._world_size
         if backend == default_backend and everyone_saves:
             if self._local_rank == 0:
@@ -338,6 +350,10 @@ class CheckpointEngine(metaclass=ABCMeta):
         handler = getattr(self, "_shm_handler", None)
         if handler is not None:
             handler.close()
+        ctl = getattr(self, "_coop_ctl", None)
+        if ctl is not None:
+            ctl.close()
+            self._coop_ctl = None
 
     def _notify_agent_to_create_saver(self):
         if self._local_rank != 0:
@@ -370,6 +386,81 @@ class CheckpointEngine(metaclass=ABCMeta):
         wait_socket_server(self._event_queue)
         logger.info(f"Update saver config: {event.__dict__}")
         self._event_queue.put(event)
+
+    # -- cooperative save of a replicated state --------------------------------------------
+    def _cooperative_by_config(self) -> bool:
+        """One shard per node, several local ranks, all holding the same state: instead of
+        the one saving rank pushing the whole image through its one PCIe link
+        (reference full_ckpt_engine.py:76-89), every local rank drains 1/n of it.
+        DLROVER_B200_COOP_DRAIN=0 (or cooperative=False) keeps the reference's policy."""
+        if not self._supports_cooperative or not dist.is_initialized():
+            return False
+        if os.getenv("DLROVER_B200_COOP_DRAIN", "1") in ("0", "false", "False"):
+            return False
+        if getattr(self, "_cooperative_arg", None) is False:
+            return False
+        return self.get_local_shard_num() == 1 and env_utils.get_local_world_size() > 1
+
+    def _cooperative(self) -> bool:
+        """Decided once, after the agent's sockets are up: needs the control segment of an
+        agent that creates one (with the reference's agent: the reference's policy)."""
+        if not self._coop_wanted:
+            return False
+        if self._coop_ctl is None:
+            self._coop_ctl = ControlSegment.attach(self.local_shard_id)
+            if self._coop_ctl is None:
+                logger.info("No control segment (reference agent?): cooperative saves are off.")
+                self._coop_wanted = False
+                return False
+        return True
+
+    def _cooperative_save(self, state_dict, conf: CheckpointConfig, blocking: bool) -> bool:
+        handler = self._shm_handler
+        local_world = env_utils.get_local_world_size()
+        leader = self._local_rank == 0
+        conf.rank = self._rank - self._local_rank  # the node's saving rank, as in the reference
+        conf.group_rank = self._group_rank
+        conf.world_size = self._world_size
+        pending = handler.pending_save()
+        if pending is not None and blocking:
+            pending.wait()
+            pending = None
+        ready = pending is None and bool(state_dict)
+        acquired = False
+        if leader and ready:
+            acquired = bool(self._shm_lock.acquire(blocking))
+            ready = acquired
+        base_seq = self._coop_ctl.coop_seq()
+        if not check_all_rank_ready(self._coop_group, ready):
+            self.is_skip = True
+            logger.info(f"Rank {self._rank} skips the cooperative save of step {conf.step}: not "
+                        "every rank is ready (the agent is persisting, or a drain is in flight).")
+            if acquired:
+                self._shm_lock.release()
+            return False
+        state_dict[DLROVER_CKPT_CONFIG_KEY] = conf
+        coop = CoopContext(self._coop_ctl, self._local_rank, local_world, base_seq,
+                           timeout=float(self._save_timeout))
+
+        def completed():
+            if acquired:
+                self._shm_lock.release()
+
+        def failed():
+            # torn segment: writing_shm stays set; only the lock goes back
+            if acquired:
+                self._shm_lock.release()
+
+        try:
+            handler.save_state_dict(state_dict, blocking=not self._async_drain or blocking,
+                                    on_complete=completed, on_error=failed,
+                                    stream=self.snapshot_stream, coop=coop)
+        except BaseException:
+            if acquired and handler.pending_save() is None and self._shm_lock.locked():
+                self._shm_lock.release()
+            raise
+        self._cached_step = conf.step
+        return True
 
     # -- memory save ---------------------------------------------------------------------
     def _is_saving_rank(self) -> bool:
@@ -446,6 +537,8 @@ class CheckpointEngine(metaclass=ABCMeta):
     def save_state_dict_to_memory(self, state_dict, conf: CheckpointConfig, blocking=False):
         """Returns True when the state dict was (or is being) written to shared
         memory, False when this rank does not save or the save was skipped."""
+        if self._cooperative():
+            return self._cooperative_save(state_dict, conf, blocking)
         if not self._is_saving_rank():
             return False
         conf.rank = self._rank
@@ -533,7 +626,8 @@ class CheckpointEngine(metaclass=ABCMeta):
         passed = verify_all_rank_step_consistent(self._loader_group, config.step)
         if not passed or config.step <= 0:
             return 0, {}
-        stats = self._shm_handler.restore_into(target_state_dict, stream=stream, strict=strict)
+        stats = self._shm_handler.restore_into(target_state_dict, stream=stream, strict=strict,
+                                               pin_after=not self._coop_wanted)
         return config.step, stats
 
     def _restore_memory_from_replica(self):
@@ -651,9 +745,14 @@ class FullCheckpointEngine(CheckpointEngine):
         sd = engine.load()
     """
 
+    _supports_cooperative = True
+
     def __init__(self, checkpoint_dir, storage, local_shard_num=1, global_shard_num=1,
                  comm_backend="", save_timeout=CheckpointConstant.SAVE_TIMEOUT, replica_count=0,
-                 async_drain=None):
+                 async_drain=None, cooperative=None):
+        self._cooperative_arg = cooperative
+        if replica_count:
+            self._cooperative_arg = False  # replica backup reads the whole segment from one rank
         if global_shard_num < local_shard_num:
             global_shard_num = local_shard_num
             logger.info(f"Set global_shard_num to {local_shard_num}.")

@@ -29,6 +29,7 @@ import atexit
 import copy
 import json
 import os
+import pickle
 import threading
 import time
 import weakref
@@ -42,6 +43,7 @@ import torch
 from . import _native as native
 from .common.constants import EventReportConstants, NodeEnv
 from .common.log import default_logger as logger
+from .common.ctl_segment import ControlSegment
 from .common.multi_process import SharedDict, SharedMemory
 
 DLROVER_CKPT_CONFIG_KEY = "_DLORVER_CKPT_CONFIG"
@@ -84,6 +86,29 @@ class CheckpointConfig:
     paths: Dict[str, str] = None  # type: ignore
 
 
+class CoopContext:
+    """One local rank's part in a cooperative save of a REPLICATED state: all
+    `n` local ranks hold the same state dict and each writes only the byte range
+    window(total) of the one image into the one segment — over its own PCIe link,
+    from a 1/n-sized arena.  `leader` (local rank 0, the reference's saving rank,
+    full_ckpt_engine.py:76-89) sizes the segment, publishes the meta and collects the
+    others' completion through the control segment's slots."""
+
+    ALIGN = 2 << 20  # slice boundaries: 2 MiB (page- and huge-page-aligned windows)
+
+    def __init__(self, ctl: ControlSegment, index: int, n: int, base_seq: int,
+                 timeout: float = 600.0):
+        self.ctl, self.index, self.n = ctl, index, n
+        self.leader = index == 0
+        self.seq = base_seq + 1
+        self.timeout = timeout
+
+    def window(self, total: int) -> Tuple[int, int]:
+        def cut(i):
+            return total if i >= self.n else (total * i // self.n) // self.ALIGN * self.ALIGN
+        return cut(self.index), cut(self.index + 1)
+
+
 # ------------------------------------------------------------------- traversal --
 
 
@@ -100,7 +125,8 @@ def _traverse_state_dict(value, visitor: Callable):
 class _Layout:
     """Result of one planning walk over a state_dict."""
 
-    __slots__ = ("meta", "total", "device_leaves", "host_leaves", "leaf_metas", "reused")
+    __slots__ = ("meta", "total", "device_leaves", "host_leaves", "leaf_metas", "reused",
+                 "extras", "shape_hash", "unchanged")
 
     def __init__(self):
         self.meta: Any = None
@@ -109,6 +135,9 @@ class _Layout:
         self.host_leaves: List[Tuple[torch.Tensor, TensorMeta]] = []
         self.leaf_metas: List[TensorMeta] = []  # every tensor leaf, traversal order
         self.reused = 0  # leaves whose TensorMeta was taken over from `prev`
+        self.extras: list = []  # non-tensor leaves, traversal order
+        self.shape_hash = 0     # hash over the keys / container kinds met by the walk
+        self.unchanged = False  # same meta tree as `prev` (keys, TensorMetas, extras)
 
 
 _IMMUTABLE_LEAVES = frozenset({int, float, str, bool, bytes, type(None), complex, torch.dtype,
@@ -129,9 +158,11 @@ def plan_layout(state_dict, prev: Optional["_Layout"] = None) -> _Layout:
     Tensor = torch.Tensor
     total = 0
     reused = 0
+    shape_hash = 0
+    extras = lay.extras
 
     def walk(value):
-        nonlocal total, reused
+        nonlocal total, reused, shape_hash
         if isinstance(value, Tensor):
             i = len(metas)
             m = prev_metas[i] if i < nprev else None
@@ -150,23 +181,42 @@ def plan_layout(state_dict, prev: Optional["_Layout"] = None) -> _Layout:
             return m
         kind = type(value)
         if kind is dict or (kind is not list and isinstance(value, Mapping)):
-            return {k: walk(v) for k, v in value.items()}
+            out = {}
+            for k, v in value.items():
+                shape_hash = hash((shape_hash, k))
+                out[k] = walk(v)
+            shape_hash = hash((shape_hash, len(out), 1))
+            return out
         if kind is list or isinstance(value, list):
+            shape_hash = hash((shape_hash, len(value), 2))
             return [walk(v) for v in value]
         # non-tensor leaf (tuples included): carried in the meta tree.  The tree is
         # pickled later, possibly on the completion thread: mutable leaves (an args
         # Namespace, user objects) are copied NOW, on the calling thread, so they are
         # captured from the same iteration as the tensors
-        if kind in _IMMUTABLE_LEAVES:
-            return value
-        try:
-            return copy.deepcopy(value)
-        except Exception:
-            return value
+        if kind not in _IMMUTABLE_LEAVES:
+            try:
+                value = copy.deepcopy(value)
+            except Exception:
+                pass
+        extras.append(value)
+        return value
 
     lay.meta = walk(state_dict)
     lay.total = total
     lay.reused = reused
+    lay.shape_hash = shape_hash
+    if prev is not None and reused == len(metas) == nprev and shape_hash == prev.shape_hash \
+            and len(extras) == len(prev.extras):
+        try:
+            # the CheckpointConfig of the save is one of the extras and differs every
+            # time: it travels separately (see _MetaPlane), everything else must be equal
+            lay.unchanged = all(
+                (isinstance(a, CheckpointConfig) and isinstance(b, CheckpointConfig)) or
+                (type(a) is type(b) and a == b)
+                for a, b in zip(extras, prev.extras))
+        except Exception:
+            lay.unchanged = False
     return lay
 
 
@@ -276,6 +326,10 @@ def _row_ranges(t: torch.Tensor, off: int, max_rows: int = 1 << 16, min_row_byte
                 break
             idx[d] = 0
     return out
+
+
+def _triples(leaves):
+    return [(t, m.offset, m.numel * m.element_size) for t, m in leaves]
 
 
 def _clip_ranges(prepared, lo: int, hi: int):
@@ -517,6 +571,119 @@ class PendingSave:
         return ok
 
 
+# ------------------------------------------------------------------ meta plane --
+
+
+def _ctl_enabled() -> bool:
+    if os.getenv("DLROVER_B200_WIRE_COMPAT", "0") == "1":
+        return False  # the peer is the reference: SharedDict only
+    return os.getenv("DLROVER_B200_CTL", "1") not in ("0", "false", "False")
+
+
+class _MetaPlane:
+    """Where the meta tree of a shard lives.  Same surface as the reference's
+    SharedDict (get / set / unlink / close; ckpt_saver.py:261, multi_process.py:579-672)
+    over two stores:
+
+      * the control segment (common/ctl_segment.py) when the agent created one: the
+        pickled tree is rewritten only when it changed, every save just flips the
+        seqlock'd header (step, writing_shm, the pickled CheckpointConfig) — no socket
+        round trip, no SharedDict.set on the steady-state save path;
+      * the agent's SharedDict otherwise (the reference's agent, or
+        DLROVER_B200_CTL=0 / DLROVER_B200_WIRE_COMPAT=1).
+    """
+
+    def __init__(self, shard_id: int, host: bool):
+        self._shard = shard_id
+        self._host = host
+        self.dict = SharedDict(name=CheckpointSharedObjPrefix.META_NAME + str(shard_id),
+                               create=host)
+        self._ctl: Optional[ControlSegment] = None
+        self._ctl_looked = False
+        self.next_unchanged = False   # set by the handler right before a steady-state set()
+        self.payload_bytes = 0
+        self.ctl_publishes = 0
+        self.dict_sets = 0
+        if host and _ctl_enabled():
+            try:
+                self._ctl = ControlSegment.create(shard_id)
+            except OSError as e:
+                logger.warning(f"no control segment for shard {shard_id}: {e}")
+            self._ctl_looked = True
+
+    @property
+    def ctl(self) -> Optional[ControlSegment]:
+        if not _ctl_enabled():
+            return None
+        if self._ctl is not None and self._ctl.stale():
+            self._ctl.close()
+            self._ctl, self._ctl_looked = None, False
+        if self._ctl is None and not self._ctl_looked:
+            self._ctl = ControlSegment.attach(self._shard)
+            self._ctl_looked = True
+        return self._ctl
+
+    def set(self, meta_dict):
+        unchanged, self.next_unchanged = self.next_unchanged, False
+        ctl = self.ctl
+        # the owner keeps a SharedDict-only peer (the reference's trainer) working:
+        # it writes through the control segment only once a trainer has used it
+        if ctl is not None and (not self._host or ctl.has_meta()):
+            if not meta_dict:
+                ctl.clear()
+                self.dict._dict = {}
+                return
+            conf = meta_dict.get(DLROVER_CKPT_CONFIG_KEY)
+            blob = None
+            if not unchanged or not ctl.has_meta():
+                rest = {k: v for k, v in meta_dict.items() if k != DLROVER_CKPT_CONFIG_KEY}
+                blob = pickle.dumps(rest, protocol=pickle.HIGHEST_PROTOCOL)
+            ok = ctl.publish(step=int(getattr(conf, "step", 0) or 0),
+                             writing=bool(getattr(conf, "writing_shm", False)),
+                             payload_bytes=int(self.payload_bytes),
+                             conf_blob=pickle.dumps(conf, protocol=pickle.HIGHEST_PROTOCOL),
+                             meta_blob=blob)
+            if ok:
+                self.ctl_publishes += 1
+                self.dict._dict = meta_dict
+                return
+            logger.warning("meta tree does not fit the control segment: using the SharedDict")
+            ctl.clear()
+        self.dict_sets += 1
+        self.dict.set(meta_dict)
+
+    def get(self, local: bool = False):
+        if local:
+            return self.dict.get(local=True)
+        ctl = self.ctl
+        if ctl is not None:
+            snap = ctl.snapshot()
+            if snap is not None:
+                _step, _writing, _payload, conf_blob, _gen, rest = snap
+                out = dict(rest)
+                conf = pickle.loads(conf_blob) if conf_blob else None
+                if conf is not None:
+                    out[DLROVER_CKPT_CONFIG_KEY] = conf
+                return out
+        return self.dict.get()
+
+    def unlink(self):
+        self.dict.unlink()
+        if self._ctl is not None and self._host:
+            self._ctl.unlink()
+
+    def close(self):
+        try:
+            self.dict.close()
+        finally:
+            if self._ctl is not None:
+                self._ctl.close()
+                self._ctl = None
+
+    def __bool__(self):
+        return True
+
+
 # --------------------------------------------------------------------- handler --
 
 
@@ -536,10 +703,10 @@ class SharedMemoryHandler:
         base = CheckpointSharedObjPrefix.SHM_NAME + str(local_rank)
         self._shm_name = f"{run_id}_{base}" if run_id else base
         self.shared_memory: Optional[SharedMemory] = None
-        self.metadata = SharedDict(name=CheckpointSharedObjPrefix.META_NAME + str(local_rank),
-                                   create=host)
+        self.metadata = _MetaPlane(local_rank, host)
         self._need_creation = True
         self._announced_once = False
+        self._meta_published = False  # the last save's meta tree reached the meta plane
         self._layout: Optional[_Layout] = None  # of the previous save (TensorMeta reuse)
         self._stager: Optional[_DeviceStager] = None
         self._pending: Optional[PendingSave] = None
@@ -703,8 +870,8 @@ class SharedMemoryHandler:
         only (cooperative save of a replicated state: every local rank drains its own
         slice of the same image over its own PCIe link): CUDA ranges are clipped to
         the window, the arena holds hi-lo bytes, only that part of the segment is
-        pinned.  Host ranges / raw chunks are written as given (the caller hands them
-        to one rank only).
+        pinned.  Host ranges are clipped the same way (parallel memcpy across the
+        ranks); raw chunks are written as given (hand them to one rank only).
         """
         keepalive = keepalive if keepalive is not None else []
         for chunk, off in raw_chunks:
@@ -720,7 +887,10 @@ class SharedMemoryHandler:
                 ptrs.append(c.data_ptr())
                 offs.append(off)
                 lens.append(nbytes)
-            native.host_pack(self.shared_memory.address, ptrs, offs, lens, _host_threads())
+            if window is not None:
+                ptrs, offs, lens = _clip_ranges((ptrs, offs, lens), window[0], window[1])
+            if ptrs:
+                native.host_pack(self.shared_memory.address, ptrs, offs, lens, _host_threads())
             del keep
         ctx, ticket = None, 0
         stager = None
@@ -861,9 +1031,27 @@ class SharedMemoryHandler:
         if ev is not None:
             (stream or torch.cuda.current_stream()).wait_event(ev)
 
+    def attach_existing(self, total: int):
+        """Map the segment another local process created (cooperative saves); it must
+        already have `total` bytes."""
+        shm = self.shared_memory
+        if shm is None or self._need_creation or shm.stale() or shm.size != total:
+            if self._stager is not None:
+                self._stager.detach()
+            if shm is not None:
+                shm.close()
+                self.shared_memory = None
+            self.init_shared_memory(create=False)
+        if self.shared_memory is None or self.shared_memory.size != total:
+            have = None if self.shared_memory is None else self.shared_memory.size
+            raise RuntimeError(f"cooperative save: the segment has {have} bytes, this rank's "
+                               f"state dict needs {total} (replicas differ?)")
+        self._buffer_size = total
+
     def save_state_dict(self, state_dict, blocking: bool = True, stream=None,
                         on_complete: Optional[Callable[[], None]] = None,
-                        on_error: Optional[Callable[[], None]] = None):
+                        on_error: Optional[Callable[[], None]] = None,
+                        coop: Optional[CoopContext] = None):
         """Serialise `state_dict` into the segment.
 
         blocking=True (the reference's semantics): returns None after every
@@ -871,18 +1059,27 @@ class SharedMemoryHandler:
         blocking=False: returns a PendingSave right after the gather kernel is
         enqueued on `stream` (default: the current stream); a completion thread
         finishes the protocol and then calls `on_complete`.
+        coop: this process writes only its slice of the image (see CoopContext); the
+        leader runs the meta protocol, the others report through the control segment.
         """
         self.wait_pending()
         lay = self._layout = plan_layout(state_dict, self._layout)
+        if coop is not None:
+            return self._save_cooperative(state_dict, lay, coop, blocking, stream, on_complete,
+                                          on_error)
         if lay.total > 0:
             self.ensure_segment(lay.total)
         meta_dict = lay.meta
         conf: CheckpointConfig = meta_dict[DLROVER_CKPT_CONFIG_KEY]
         conf.writing_shm = True
+        unchanged = lay.unchanged and self._meta_published
+        self._meta_published = False
+        self.metadata.payload_bytes = lay.total
 
         def announce():
             report_local_event(EventReportConstants.TYPE_INFO, str(conf.rank),
                                EventReportConstants.ACTION_MEM_CKPT_START, f"step={conf.step}")
+            self.metadata.next_unchanged = unchanged
             self.metadata.set(meta_dict)
 
         # Host-resident leaves are written by this thread right now, so the agent
@@ -901,23 +1098,87 @@ class SharedMemoryHandler:
 
         def finish():
             conf.writing_shm = False
+            self.metadata.next_unchanged = True  # the tree went out with the announcement
             self.metadata.set(meta_dict)
+            self._meta_published = True
             report_local_event(EventReportConstants.TYPE_INFO, str(conf.rank),
                                EventReportConstants.ACTION_MEM_CKPT_COMPLETE,
                                f"step={conf.step}")
             if on_complete is not None:
                 on_complete()
 
-        def triples(leaves):
-            return [(t, m.offset, m.numel * m.element_size) for t, m in leaves]
-
         # the tensors must outlive the gather kernel
         keepalive = [state_dict] if lay.device_leaves else []
-        return self.write_ranges(triples(lay.device_leaves), triples(lay.host_leaves),
+        return self.write_ranges(_triples(lay.device_leaves), _triples(lay.host_leaves),
                                  blocking=blocking, stream=stream, finish=finish,
                                  keepalive=keepalive,
                                  pre_drain=announce if defer_announce else None,
                                  on_error=on_error)
+
+    def _save_cooperative(self, state_dict, lay: _Layout, coop: CoopContext, blocking, stream,
+                          on_complete, on_error):
+        meta_dict = lay.meta
+        conf: CheckpointConfig = meta_dict[DLROVER_CKPT_CONFIG_KEY]
+        total = lay.total
+        if coop.leader:
+            try:
+                if total > 0:
+                    self.ensure_segment(total)
+                conf.writing_shm = True
+                self.metadata.payload_bytes = total
+                self.metadata.next_unchanged = lay.unchanged and self._meta_published
+                self._meta_published = False
+                report_local_event(EventReportConstants.TYPE_INFO, str(conf.rank),
+                                   EventReportConstants.ACTION_MEM_CKPT_START,
+                                   f"step={conf.step}")
+                self.metadata.set(meta_dict)  # before any rank touches the segment
+                self._announced_once = True
+            except BaseException:
+                coop.ctl.next_coop_seq(aborted=True)  # do not leave the others waiting
+                raise
+            coop.ctl.next_coop_seq()
+        else:
+            if not coop.ctl.wait_coop_open(coop.seq, coop.timeout):
+                raise RuntimeError("cooperative save: the leader aborted")
+            if total > 0:
+                self.attach_existing(total)
+        window = coop.window(total)
+
+        def finish():
+            coop.ctl.slot_set(coop.index, coop.seq, ok=True)
+            if coop.leader:
+                if not coop.ctl.wait_slots(coop.n, coop.seq, coop.timeout):
+                    raise RuntimeError("cooperative save: a local rank failed or did not "
+                                       f"report its slice within {coop.timeout:.0f}s")
+                conf.writing_shm = False
+                self.metadata.next_unchanged = True
+                self.metadata.set(meta_dict)
+                self._meta_published = True
+                report_local_event(EventReportConstants.TYPE_INFO, str(conf.rank),
+                                   EventReportConstants.ACTION_MEM_CKPT_COMPLETE,
+                                   f"step={conf.step}")
+            if on_complete is not None:
+                on_complete()
+
+        def failed():
+            try:
+                coop.ctl.slot_set(coop.index, coop.seq, ok=False)
+            finally:
+                if on_error is not None:
+                    on_error()
+
+        keepalive = [state_dict] if lay.device_leaves else []
+        if total == 0:
+            finish()
+            return None
+        try:
+            return self.write_ranges(_triples(lay.device_leaves), _triples(lay.host_leaves),
+                                     blocking=blocking, stream=stream, finish=finish,
+                                     keepalive=keepalive, on_error=failed, window=window)
+        except BaseException:
+            if self._pending is None:  # raised before a completion thread took over
+                coop.ctl.slot_set(coop.index, coop.seq, ok=False)
+            raise
 
     def _run_completion(self, pending: PendingSave):
         pending._complete()
@@ -944,7 +1205,8 @@ class SharedMemoryHandler:
                            f"step={config.step}")
         return state_dict
 
-    def restore_into(self, target, stream=None, strict: bool = True) -> Dict[str, float]:
+    def restore_into(self, target, stream=None, strict: bool = True,
+                     pin_after: bool = True) -> Dict[str, float]:
         """Scatter the in-memory checkpoint straight into the live tensors of
         `target` (same tree structure as what was saved; extra keys on either
         side raise when strict).  CUDA leaves: one DMA fill of the arena + one
@@ -1014,16 +1276,18 @@ class SharedMemoryHandler:
                 prepared = stager.prepare_ranges(
                     [(t, m.offset, m.numel * m.element_size) for t, m in device_pairs], [],
                     for_write=True)
-                stager.attach(self.shared_memory)
+                if stager._attached is None:
+                    stager.attach(self.shared_memory)
                 if stream is None:
                     stream = torch.cuda.current_stream(stager.device_index)
                 plan = stager.plan_for(prepared, role="restore", stream=stream)
-                stats.update(self._run_restore(stager, plan, stream))
+                stats.update(self._run_restore(stager, plan, stream, pin_after=pin_after))
         return stats
 
     DIRECT_RESTORE_MIN_SPAN = 1 << 20  # average span size from which in-place restore wins
 
-    def _run_restore(self, stager: _DeviceStager, plan, stream) -> Dict[str, float]:
+    def _run_restore(self, stager: _DeviceStager, plan, stream,
+                     pin_after: bool = True) -> Dict[str, float]:
         """Few large spans: H2D DMA straight into the targets.  Many small ones: one
         DMA per merged segment run into the arena + one scatter kernel.
         DLROVER_B200_RESTORE=direct|arena overrides the choice."""
@@ -1042,7 +1306,8 @@ class SharedMemoryHandler:
         self.last_restore_stats = {"device_bytes": float(plan.payload_bytes), "fill_ms": fill,
                                    "scatter_ms": scatter, "direct": float(direct),
                                    "staged": float(staged), "wall_ms": wall_ms}
-        stager.pin_in_background()  # the next save wants plain DMA
+        if pin_after:
+            stager.pin_in_background()  # the next save wants plain DMA
         return dict(self.last_restore_stats)
 
     def read_ranges(self, device_ranges, stream=None) -> Dict[str, float]:
@@ -1062,7 +1327,8 @@ class SharedMemoryHandler:
                 raise ValueError("read_ranges: range does not fit the segment / the tensor")
         stager = self._stager_for([r[0] for r in device_ranges])
         prepared = stager.prepare_ranges(device_ranges, [], for_write=True)
-        stager.attach(self.shared_memory)
+        if stager._attached is None:
+            stager.attach(self.shared_memory)
         if stream is None:
             stream = torch.cuda.current_stream(stager.device_index)
         plan = stager.plan_for(prepared, role="restore", stream=stream)

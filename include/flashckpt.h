@@ -92,7 +92,8 @@ int fc_set_arena_limit(fc_ctx* ctx, uint64_t bytes);
 int fc_host_register(fc_ctx* ctx, void* host, uint64_t bytes, int prefault_threads);
 int fc_host_unregister(fc_ctx* ctx, void* host);
 /* The same pinning, off the caller's thread: a library thread registers the range
- * slice by slice (slice_bytes, 0 = 64 MiB; no DMA of this library ever straddles two
+ * slice by slice (slice_bytes, 0 = 256 MiB, a pause after each so that the caller's own
+ * CUDA calls get the driver lock in between; no DMA of this library ever straddles two
  * slices) and the call returns at once.  Until fc_host_ready() answers FC_OK, saves
  * and restores that touch the range go through the staged path below — so neither the
  * first save of a run nor the restore of a restarted trainer waits 3-6 s for

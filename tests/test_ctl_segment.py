@@ -1,0 +1,173 @@
+"""Control segment (common/ctl_segment.py) and the meta plane built on it
+(shm_handler._MetaPlane): SURVEY §8 f.4 — the meta tree of a shard in shared memory,
+guarded by a seqlock, instead of two pickled SharedDict.set round trips per save
+(reference ckpt_saver.py:315-327, multi_process.py:579-672)."""
+
+import pickle
+import threading
+import time
+
+import pytest
+import torch
+
+from dlrover_b200.common import ctl_segment as cs
+from dlrover_b200.shm_handler import (DLROVER_CKPT_CONFIG_KEY, CheckpointConfig, CoopContext,
+                                      SharedMemoryHandler)
+
+
+def test_publish_snapshot_and_generations(run_env):
+    owner = cs.ControlSegment.create(3)
+    try:
+        assert cs.ControlSegment.attach(4) is None
+        peer = cs.ControlSegment.attach(3)
+        assert peer is not None and peer.snapshot() is None and not peer.has_meta()
+        tree = {"model": {"w": ("meta", 1, 2)}, "lr": 0.1}
+        conf = pickle.dumps({"step": 5})
+        assert peer.publish(step=5, writing=True, payload_bytes=99, conf_blob=conf,
+                            meta_blob=pickle.dumps(tree))
+        step, writing, payload, conf_blob, gen, meta = owner.snapshot()
+        assert (step, writing, payload, gen) == (5, True, 99, 1) and meta == tree
+        assert pickle.loads(conf_blob) == {"step": 5}
+        # header-only update: same generation, the cached tree object is reused
+        assert peer.publish(step=5, writing=False, payload_bytes=99, conf_blob=conf)
+        step, writing, _, _, gen2, meta2 = owner.snapshot()
+        assert (step, writing, gen2) == (5, False, 1) and meta2 is meta
+        # a blob that does not fit is refused, nothing changes
+        assert not peer.publish(step=6, writing=True, payload_bytes=1, conf_blob=conf,
+                                meta_blob=b"x" * (peer.meta_capacity + 1))
+        assert owner.snapshot()[0] == 5
+        # a writer that died mid-update (odd seq) is taken over by the next one
+        peer._put(cs._OFF_SEQ, peer._u64(cs._OFF_SEQ) + 1)
+        assert owner.snapshot(timeout=0.05) is None
+        assert peer.publish(step=7, writing=False, payload_bytes=1, conf_blob=conf,
+                            meta_blob=pickle.dumps({"new": 1}))
+        assert owner.snapshot()[0] == 7 and owner.snapshot()[5] == {"new": 1}
+        owner.clear()
+        assert peer.snapshot() is None
+        peer.close()
+    finally:
+        owner.unlink()
+        owner.close()
+
+
+def test_readers_never_see_a_torn_header(run_env):
+    owner = cs.ControlSegment.create(0)
+    reader = cs.ControlSegment.attach(0)
+    stop = threading.Event()
+    bad = []
+
+    def read_loop():
+        while not stop.is_set():
+            snap = reader.snapshot()
+            if snap is None:
+                continue
+            step, writing, payload, conf_blob, gen, meta = snap
+            if pickle.loads(conf_blob) != step or payload != step * 3 or meta != {"s": gen}:
+                bad.append(snap)
+
+    t = threading.Thread(target=read_loop)
+    t.start()
+    try:
+        for step in range(1, 400):
+            blob = pickle.dumps({"s": step // 2 + 1}) if step % 2 == 0 or step == 1 else None
+            owner.publish(step=step, writing=bool(step & 1), payload_bytes=step * 3,
+                          conf_blob=pickle.dumps(step), meta_blob=blob)
+    finally:
+        stop.set()
+        t.join()
+        reader.close()
+        owner.unlink()
+        owner.close()
+    assert not bad
+
+
+def test_cooperative_handshake_and_slots(run_env):
+    ctl = cs.ControlSegment.create(0)
+    try:
+        base = ctl.coop_seq()
+        ctxs = [CoopContext(ctl, i, 4, base) for i in range(4)]
+        total = 10 * (2 << 20) + 12345
+        wins = [c.window(total) for c in ctxs]
+        assert wins[0][0] == 0 and wins[-1][1] == total
+        assert all(a[1] == b[0] for a, b in zip(wins, wins[1:]))
+        assert all(w[0] % (2 << 20) == 0 for w in wins)
+        assert CoopContext(ctl, 1, 2, base).window(100) == (0, 100)  # tiny: all in the last slice
+        with pytest.raises(TimeoutError):
+            ctl.wait_coop_open(base + 1, timeout=0.05)
+        threading.Timer(0.05, ctl.next_coop_seq).start()
+        assert ctl.wait_coop_open(base + 1, timeout=5) is True
+        seq = base + 1
+        assert not ctl.wait_slots(4, seq, timeout=0.05)
+        for i in range(4):
+            ctl.slot_set(i, seq)
+        assert ctl.wait_slots(4, seq, timeout=1)
+        ctl.slot_set(2, seq + 1, ok=False)
+        for i in (0, 1, 3):
+            ctl.slot_set(i, seq + 1)
+        assert not ctl.wait_slots(4, seq + 1, timeout=1)     # a rank reported a failure
+        assert ctl.next_coop_seq(aborted=True) == seq + 1
+        assert ctl.wait_coop_open(seq + 1, timeout=1) is False
+    finally:
+        ctl.unlink()
+        ctl.close()
+
+
+def _save(trainer, sd, step):
+    full = dict(sd)
+    full[DLROVER_CKPT_CONFIG_KEY] = CheckpointConfig(step=step, paths={"m": f"/x/{step}"})
+    trainer.save_state_dict(full)
+
+
+def test_steady_state_saves_never_touch_the_shared_dict(run_env):
+    agent = SharedMemoryHandler(0, host=True)      # creates the control segment
+    trainer = SharedMemoryHandler(0, host=False)
+    try:
+        sd = {"w": torch.arange(1000, dtype=torch.float32), "opt": {"lr": 0.1, "step": 1}}
+        ctl = agent.metadata.ctl
+        assert ctl is not None and trainer.metadata.ctl is not None
+        for step in (1, 2, 3):
+            sd["w"].add_(1)
+            _save(trainer, sd, step)
+        assert trainer.metadata.dict_sets == 0 and trainer.metadata.ctl_publishes == 6
+        assert ctl._u64(cs._OFF_META_GEN) == 1           # tree pickled once, header flipped 6x
+        back = agent.load_state_dict()
+        conf = back[DLROVER_CKPT_CONFIG_KEY]
+        assert conf.step == 3 and conf.paths == {"m": "/x/3"} and conf.writing_shm is False
+        assert torch.equal(back["w"], sd["w"]) and back["opt"] == {"lr": 0.1, "step": 1}
+        del back
+        # a non-tensor leaf changes (lr schedule): the tree goes out again
+        sd["opt"]["lr"] = 0.05
+        _save(trainer, sd, 4)
+        assert ctl._u64(cs._OFF_META_GEN) == 2
+        assert agent.load_state_dict()["opt"]["lr"] == 0.05
+        # a shape changes: new layout, new tree, segment re-created, agent follows
+        sd["w"] = torch.ones(500)
+        _save(trainer, sd, 5)
+        back = agent.load_state_dict()
+        assert back["w"].shape == (500,) and back[DLROVER_CKPT_CONFIG_KEY].step == 5
+        del back
+        assert trainer.metadata.dict_sets == 0
+        # the agent forgets the checkpoint ("node replaced"): both sides see nothing
+        agent.metadata.set({})
+        assert trainer.load_state_dict() == {} and agent.no_checkpoint_state()
+    finally:
+        trainer.close()
+        agent.unlink()
+        agent.close()
+
+
+def test_without_a_control_segment_the_shared_dict_is_used(run_env, monkeypatch):
+    monkeypatch.setenv("DLROVER_B200_CTL", "0")
+    agent = SharedMemoryHandler(0, host=True)
+    trainer = SharedMemoryHandler(0, host=False)
+    try:
+        assert agent.metadata.ctl is None and trainer.metadata.ctl is None
+        sd = {"w": torch.arange(10, dtype=torch.float32)}
+        _save(trainer, sd, 1)
+        _save(trainer, sd, 2)
+        assert trainer.metadata.dict_sets == 4 and trainer.metadata.ctl_publishes == 0
+        assert agent.load_state_dict()[DLROVER_CKPT_CONFIG_KEY].step == 2
+    finally:
+        trainer.close()
+        agent.unlink()
+        agent.close()

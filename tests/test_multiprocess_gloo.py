@@ -52,7 +52,54 @@ def _worker(rank, world, port, run_id, ckpt_dir, mode, out_dir):
             result["disk_ok"] = bool(torch.equal(mine["w"], sd["w"]))
             result["ready_all"] = bool(check_all_rank_ready(None, True))
             result["ready_one_not"] = bool(check_all_rank_ready(None, rank != 1))
-        else:  # replicated: only local rank 0 writes
+        elif mode == "cooperative":
+            # replicated state, every local rank writes its slice of the ONE image
+            ckpt = DdpCheckpointer(ckpt_dir)
+            eng = ckpt.engine
+            result["coop"] = bool(eng._cooperative())
+            g = torch.Generator().manual_seed(5)
+            sd = {"a": torch.randn(700_001, generator=g), "step": 3,
+                  "b": [torch.arange(1_500_000, dtype=torch.int32), torch.ones(3)],
+                  "c": torch.randn(2_000_003, generator=g).to(torch.bfloat16)}
+            want = {k: (v.clone() if torch.is_tensor(v) else v) for k, v in sd.items() if k != "b"}
+            for step in (5, 6):      # second save: steady state (meta tree unchanged)
+                sd["a"].add_(1.0)
+                want["a"] = sd["a"].clone()
+                ckpt.save_checkpoint(step, sd, storage_type=StorageType.MEMORY)
+                ckpt.wait_memory_save()
+                dist.barrier()
+                back = ckpt.load_checkpoint()
+                result[f"mem_ok_{step}"] = bool(
+                    torch.equal(back["a"], want["a"]) and torch.equal(back["c"], want["c"])
+                    and torch.equal(back["b"][0], sd["b"][0]) and back["step"] == 3)
+                del back
+                dist.barrier()
+            plane = eng._shm_handler.metadata
+            result["dict_sets"], result["ctl_publishes"] = plane.dict_sets, plane.ctl_publishes
+            shm = eng._shm_handler.shared_memory
+            result["segment"] = shm.name
+            total = shm.size
+            ctx = __import__("dlrover_b200.shm_handler", fromlist=["CoopContext"]).CoopContext(
+                None, rank, world, 0)
+            result["window"] = ctx.window(total)
+            result["total"] = total
+            ckpt.save_checkpoint(7, sd, storage_type=StorageType.DISK)
+            if rank == 0:
+                ckpt.wait_latest_checkpoint(timeout=90)
+            dist.barrier()
+            result["files"] = sorted(os.listdir(os.path.join(ckpt_dir, "7")))
+            mine = torch.load(os.path.join(ckpt_dir, "7", "rank_0.pt"))
+            result["disk_ok"] = bool(torch.equal(mine["a"], sd["a"]) and
+                                     torch.equal(mine["c"], sd["c"]))
+            # in-place restore into live tensors on every rank
+            live = {k: (torch.zeros_like(v) if torch.is_tensor(v) else v) for k, v in sd.items()
+                    if k != "b"}
+            live["b"] = [torch.zeros_like(sd["b"][0]), torch.zeros(3)]
+            result["restored_step"] = ckpt.load_checkpoint_into(live)
+            result["restore_ok"] = bool(torch.equal(live["a"], sd["a"]) and
+                                        torch.equal(live["b"][0], sd["b"][0]))
+        else:  # replicated, the reference's policy: only local rank 0 writes
+            os.environ["DLROVER_B200_COOP_DRAIN"] = "0"
             ckpt = DdpCheckpointer(ckpt_dir)
             eng = ckpt.engine
             result["saving_ranks"] = eng._saving_ranks
@@ -102,6 +149,26 @@ def test_every_rank_is_a_shard():
         assert res["tracker"] == "4"
         assert res["files"] == ["rank_0.pt", "rank_1.pt"]
         assert res["ready_all"] is True and res["ready_one_not"] is False
+
+
+@pytest.mark.timeout(300)
+def test_replicated_state_is_saved_cooperatively():
+    """Default for replicated state on a multi-rank node: both ranks write their slice of
+    the one image into ckpt_shm_0; one meta, one file on disk, identical to what a single
+    saving rank would have produced (the tensors come back bit-exact on both ranks)."""
+    r0, r1 = _run("cooperative")
+    for res in (r0, r1):
+        assert res["coop"] is True
+        assert res["mem_ok_5"] and res["mem_ok_6"] and res["disk_ok"] and res["restore_ok"]
+        assert res["restored_step"] == 7
+        assert res["files"] == ["rank_0.pt"]
+        assert res["segment"].endswith("ckpt_shm_0")
+    # the two windows tile the segment at a 2 MiB boundary
+    (a0, a1), (b0, b1) = r0["window"], r1["window"]
+    assert a0 == 0 and a1 == b0 and b1 == r0["total"] and a1 % (2 << 20) == 0 and a1 > 0
+    # meta plane: no SharedDict.set at all, the control segment carries the saves
+    assert r0["dict_sets"] == 0 and r0["ctl_publishes"] == 4   # 2 saves x (announce, finish)
+    assert r1["dict_sets"] == 0 and r1["ctl_publishes"] == 0   # followers publish nothing
 
 
 @pytest.mark.timeout(300)
