@@ -278,6 +278,32 @@ def workload_config(S, world, scale):
 # --------------------------------------------------------------------- our arm --
 
 
+def new_agent_namespace(tag: str):
+    """Every leg gets its own IPC namespace (socket dir, segment names) and therefore its
+    own saver daemon, forked by local rank 0 when the leg's engine is created."""
+    from dlrover_b200.flash_checkpoint.engine import CheckpointEngine
+
+    os.environ["TORCHELASTIC_RUN_ID"] = f"fcbench{os.getppid()}{tag}"
+    CheckpointEngine.saver_proc = None
+    return f"/tmp/fc_bench_{os.environ['TORCHELASTIC_RUN_ID']}"
+
+
+def drop_segment(engine):
+    """The saver daemon unlinks the segments when this process ends; do not rely on it
+    alone — the driver runs several bench processes back to back on one box."""
+    import torch.distributed as dist
+
+    if dist.is_initialized():
+        dist.barrier()
+    shm = engine._shm_handler.shared_memory
+    if shm is not None and engine._local_rank == engine.local_shard_id:
+        try:
+            shm.unlink()
+        except (FileNotFoundError, OSError):
+            pass
+    engine.close()
+
+
 def run_ours(args):
     rank, local, world = dist_env()
     os.environ.setdefault("TORCHELASTIC_RUN_ID", f"fcbench{os.getppid()}")
@@ -408,23 +434,31 @@ def run_ours(args):
     if not args.no_stall:
         stall = measure_stall(ckpt, sd, S, dev, world)
 
+    # ---- leg 3b: restore in a FRESH process (a restarted trainer), N=1 only ------------------
+    fresh = None
+    if world == 1:
+        fresh = measure_fresh_restore(ckpt, sd, S, ckpt_dir)
+
     # ---- leg 4: cpu_baseline (rank 0, N=1 only) ------------------------------------------
     cpu_base = None
     if world == 1:
         cpu_base = measure_cpu_baseline(sd, S)
 
+    drop_segment(ckpt.engine)
+
+    # ---- leg 5 (N>1): the SAME replicated state saved cooperatively -----------------------
+    coop = None
+    if world > 1:
+        coop = measure_cooperative(args, sd, S, world, dev)
+    # ---- leg 6 (N>1): BASELINE configs[2] — FSDP full-shard, every rank its local shard ----
+    fsdp = None
+    if world > 1 and not os.getenv("BENCH_NO_FSDP"):
+        del sd
+        torch.cuda.empty_cache()
+        fsdp = measure_fsdp(args, world, rank, local, dev)
+
     if world > 1:
         dist.barrier()
-    # the saver daemon unlinks the segments when this process ends; do not rely on it
-    # alone — the driver runs several bench processes back to back on one box and
-    # 16 GB per rank of leaked tmpfs would add up
-    shm = ckpt.engine._shm_handler.shared_memory
-    if shm is not None:
-        try:
-            shm.unlink()
-        except (FileNotFoundError, OSError):
-            pass
-    ckpt.engine.close()
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -440,9 +474,15 @@ def run_ours(args):
                             "the host buffer is the shm segment the drain fills"},
             "stall_ms": stall,
             "restore": restore,
+            "restore_fresh_process": fresh,
+            "ddp_cooperative": coop,
+            "fsdp": fsdp,
             "roofline": {"bound": "hbm", "kernel": "fc_copy_tma<0> (gather/pack)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": ncu_traffic(),
+                         "traffic_source": "static: profiles/pack_kernel_ncu.json (one ncu --set "
+                                           "full capture of this kernel on this workload, "
+                                           "dram__bytes_read.sum + dram__bytes_write.sum)",
                          "algorithmic_bytes_per_launch": 2 * S, "avg_launch_ms": pack_ms,
                          "peak_source": peak_src},
             "drain": {"avg_ms": drain_ms, "GBps": S / drain_ms / 1e6, "bound": "PCIe Gen5 x16"},
@@ -455,8 +495,174 @@ def run_ours(args):
         }
         print(json.dumps(line), flush=True)
     if world > 1:
+        dist.barrier()  # nothing else writes to stdout while rank 0 prints
         dist.destroy_process_group()
     return 0
+
+
+def measure_cooperative(args, sd, S, world, dev):
+    """The path configs[1] shards by at N>1: the state is REPLICATED (DDP), the reference
+    lets local rank 0 alone write it (one PCIe link, full_ckpt_engine.py:76-89); here all
+    local ranks drain 1/N of the same image into the same segment."""
+    import torch
+
+    from dlrover_b200.flash_checkpoint.api import DdpCheckpointer, StorageType
+
+    ckpt = DdpCheckpointer(new_agent_namespace("c"))  # local_shard_num=1: one image per node
+    assert ckpt.engine._cooperative(), "cooperative saves are off"
+
+    def step(i):
+        t0 = time.perf_counter()
+        ckpt.save_checkpoint(i, sd, storage_type=StorageType.MEMORY)
+        call = time.perf_counter() - t0
+        ckpt.wait_memory_save()
+        return call
+
+    t0 = time.perf_counter()
+    step(1)
+    first = time.perf_counter() - t0
+    ckpt.engine.wait_segment_pinned(120)
+    for i in range(max(args.warmup, 3)):
+        step(2 + i)
+    barrier_sync(world)
+    t0 = time.perf_counter()
+    calls = [step(100 + i) for i in range(args.steps)]
+    barrier_sync(world)
+    dt = max_over_ranks(time.perf_counter() - t0, world, dev)
+    timings = ckpt.engine.last_save_timings() or (None, None, None)
+    # every rank checks ITS slice of the one image against its own replica
+    import numpy as np
+
+    shm = ckpt.engine._shm_handler.shared_memory
+    img = np.frombuffer(shm.buf, dtype=np.uint8)
+    lo, hi = __import__("dlrover_b200.shm_handler", fromlist=["CoopContext"]).CoopContext(
+        None, ckpt.engine._local_rank, world, 0).window(S)
+    ok, off = True, 0
+    for t in sd.values():
+        n = t.numel() * t.element_size()
+        a, b = max(off, lo), min(off + n, hi)
+        if b > a:
+            m = min(b - a, 1 << 18)
+            flat = t.view(-1).view(torch.uint8)
+            ok = ok and np.array_equal(img[a:a + m], flat[a - off:a - off + m].cpu().numpy())
+        off += n
+    ok = bool(sum_over_ranks(0.0 if ok else 1.0, world, dev) == 0)
+    del img
+    out = {"value": S * args.steps / dt / 1e9, "unit": UNIT,
+           "what": f"ONE {S / 1e9:.2f} GB image (replicated state) per node, {world} ranks each "
+                   "gather + drain 1/N of it into the same segment; value = image bytes / wall "
+                   "time of save_checkpoint(MEMORY)+wait_memory_save (slowest rank)",
+           "ms_per_save": dt / args.steps * 1e3, "host_call_ms": sum(calls) / len(calls) * 1e3,
+           "first_save_s": first, "slice_bytes": hi - lo,
+           "pack_ms_slice": timings[0], "drain_ms_slice": timings[1],
+           "single_link_reference_policy_ms": S / 55.5e9 * 1e3,
+           "image_matches_replicas": ok}
+    drop_segment(ckpt.engine)
+    return out
+
+
+def measure_fsdp(args, world, rank, local, dev):
+    """BASELINE configs[2]: Llama-3-8B FSDP full-shard — every rank saves ITS shard (bf16
+    weights + fp32 AdamW moments, rows sharded 1/N) through FsdpCheckpointEngine /
+    torch.distributed.checkpoint, with fresh tensors at every save (fc_plan_update)."""
+    import torch
+    import torch.distributed as dist
+    from torch.distributed.device_mesh import init_device_mesh
+
+    from dlrover_b200 import shapes
+    from dlrover_b200.common.constants import CheckpointConstant
+    from dlrover_b200.common.storage import PosixDiskStorage
+    from dlrover_b200.flash_checkpoint.fsdp_engine import FsdpCheckpointEngine
+
+    mesh = init_device_mesh("cuda", (world,))
+    factory = shapes.ShardedStateFactory(
+        shapes.scale_shapes(shapes.llama3_8b_shapes(), args.scale), world, rank, dev, mesh)
+    states = [factory.build(0), factory.build(1)]
+    ckpt_dir = new_agent_namespace("f")
+    engine = FsdpCheckpointEngine(ckpt_dir, PosixDiskStorage())
+    name = CheckpointConstant.MODEL_STATES_NAME
+    S_rank = factory.local_bytes
+
+    def step(i):
+        t0 = time.perf_counter()
+        ok = engine.save_to_memory(i, states[i & 1], {name: os.path.join(ckpt_dir, str(i))})
+        call = time.perf_counter() - t0
+        engine.wait_memory_save()
+        assert ok
+        return call
+
+    t0 = time.perf_counter()
+    step(1)
+    first = time.perf_counter() - t0
+    engine.wait_segment_pinned(120)
+    for i in range(max(args.warmup, 3)):
+        step(2 + i)
+    barrier_sync(world)
+    t0 = time.perf_counter()
+    calls = [step(100 + i) for i in range(args.steps)]
+    barrier_sync(world)
+    dt = max_over_ranks(time.perf_counter() - t0, world, dev)
+    timings = engine.last_save_timings() or (None, None, None)
+    total = sum_over_ranks(float(S_rank), world, dev)
+    # spot check: the items of this rank's segment are the local shards of the last save
+    import numpy as np
+
+    last = states[(100 + args.steps - 1) & 1]
+    meta = engine._shm_handler.metadata.get()["dcp_metadata"]
+    img = np.frombuffer(engine._shm_handler.shared_memory.buf, dtype=np.uint8)
+    locals_ = factory.local_tensors(last)
+    ok, checked = True, 0
+    for index, info in meta.storage_data.items():
+        if info.relative_path != f"__{rank}_0.distcp" or index.fqn not in locals_ or not info.length:
+            continue
+        t = locals_[index.fqn]
+        m = min(info.length, 1 << 16)
+        ok = ok and np.array_equal(img[info.offset:info.offset + m],
+                                   t.reshape(-1).view(torch.uint8)[:m].cpu().numpy())
+        checked += 1
+    del img
+    ok = bool(sum_over_ranks(0.0 if (ok and checked) else 1.0, world, dev) == 0)
+    out = {"value": total * args.steps / dt / 1e9, "unit": UNIT,
+           "what": "Llama-3-8B FSDP full-shard (BASELINE configs[2]): per rank 1/N of the bf16 "
+                   "weights and of the fp32 AdamW moments as DTensor shards, saved through "
+                   "FsdpCheckpointEngine.save_to_memory (torch DCP planning + SharedMemoryWriter: "
+                   "one plan re-target, one gather kernel, one drain per rank), fresh tensors at "
+                   "every save; value = bytes of all ranks / wall time (slowest rank)",
+           "payload_bytes_per_rank": S_rank, "payload_bytes_total": total,
+           "ms_per_save": dt / args.steps * 1e3,
+           "host_call_ms": sum(calls) / len(calls) * 1e3,
+           "host_call_ms_max": max(calls) * 1e3, "first_save_s": first,
+           "pack_ms": timings[0], "drain_ms": timings[1], "items_checked": checked,
+           "segment_matches_local_shards": ok}
+    drop_segment(engine)
+    return out
+
+
+def measure_fresh_restore(ckpt, sd, S, ckpt_dir):
+    """A restarted trainer: new process, attaches to the segment the dead one left in
+    shared memory, restores 16 GB into live tensors.  Ours (staged bounce slots, no 16 GB
+    cudaHostRegister up front) vs the reference's way (CPU views on the pageable segment +
+    per-tensor copy_)."""
+    import torch
+
+    keys = list(sd)
+    probe = {k: int(sd[k].view(-1).view(torch.int16)[:4096].to(torch.int64).sum().item())
+             for k in (keys[0], keys[len(keys) // 2], keys[-1])}
+    spec = {"probe": probe, "ckpt_dir": ckpt_dir, "scale": float(os.getenv("BENCH_SCALE", "1.0"))}
+    out = {}
+    for mode in ("ours", "reference_style"):
+        env = dict(os.environ, FC_FRESH_SPEC=json.dumps(spec), FC_FRESH_MODE=mode)
+        t0 = time.time()
+        p = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "fresh_restore.py")],
+                           env=env, capture_output=True, text=True, timeout=600)
+        wall = time.time() - t0
+        try:
+            rec = json.loads(p.stdout.strip().split("\n")[-1])
+        except Exception:
+            rec = {"error": (p.stderr or p.stdout)[-800:]}
+        rec["process_wall_s"] = wall
+        out[mode] = rec
+    return out
 
 
 def measure_stall(ckpt, sd, S, dev, world):

@@ -6,8 +6,9 @@ trainer re-sends the whole pickled tree twice per save over a unix socket
 shm segment next to the data segment — ``[<run_id>_]ckpt_ctl_<shard>`` — holds
 
   * a header guarded by a seqlock: step, "segment is being written" flag, payload
-    size, the pickled CheckpointConfig of the current save (a few hundred bytes) and
-    the generation / length of the meta area;
+    size, the length of the per-save blob (the pickled CheckpointConfig of the current
+    save and other small per-save objects, up to 1 MiB) and the generation / length of
+    the meta area;
   * one slot per local rank for cooperative saves (each rank reports the step whose
     slice it has landed in the data segment);
   * the pickled meta tree, rewritten only when the structure of the state dict (or a
@@ -36,10 +37,12 @@ VERSION = 1
 HEADER_BYTES = 4096
 SLOT_BYTES = 64
 MAX_SLOTS = 64
-META_OFFSET = HEADER_BYTES + SLOT_BYTES * MAX_SLOTS  # 8192
-CONF_OFFSET = 128
-CONF_CAPACITY = HEADER_BYTES - CONF_OFFSET
-DEFAULT_BYTES = 8 << 20
+# the per-save ("volatile") blob: the pickled CheckpointConfig plus whatever small
+# objects change at every save (FSDP: the non-sharded entries of the state dict)
+CONF_OFFSET = HEADER_BYTES + SLOT_BYTES * MAX_SLOTS  # 8192
+CONF_CAPACITY = 1 << 20
+META_OFFSET = CONF_OFFSET + CONF_CAPACITY
+DEFAULT_BYTES = 16 << 20
 
 # header field offsets (little-endian u64 unless noted)
 _OFF_MAGIC, _OFF_VERSION, _OFF_SEQ, _OFF_STEP, _OFF_WRITING = 0, 8, 16, 24, 32
@@ -72,7 +75,7 @@ class ControlSegment:
         """Create (or adopt, if a previous agent left one) the shard's control segment."""
         name = ctl_name(shard_id)
         try:
-            shm = SharedMemory(name=name, create=True, size=max(nbytes, META_OFFSET + 4096))
+            shm = SharedMemory(name=name, create=True, size=max(nbytes, META_OFFSET + (1 << 20)))
             fresh = True
         except FileExistsError:
             shm = SharedMemory(name=name)
@@ -104,6 +107,10 @@ class ControlSegment:
     @property
     def meta_capacity(self) -> int:
         return self._shm.size - META_OFFSET
+
+    @property
+    def conf_capacity(self) -> int:
+        return CONF_CAPACITY
 
     def close(self):
         self._buf = None

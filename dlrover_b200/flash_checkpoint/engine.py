@@ -108,6 +108,19 @@ def check_all_rank_ready(group: Optional[dist.ProcessGroup], ready: bool):
     return not_ready == 0
 
 
+def all_reduce_flags(group: Optional[dist.ProcessGroup], flags: List[int]) -> List[int]:
+    """SUM all-reduce of a few small non-negative ints (readiness + "my plan changed"
+    in ONE collective), on the side stream like check_all_rank_ready."""
+    if not group and not dist.is_initialized():
+        return list(flags)
+    device = _sync_device(dist.get_backend(group))
+    with _OffTrainingStream(device):
+        t = torch.tensor(flags, dtype=torch.int32, device=device)
+        dist.all_reduce(t, group=group)
+        out = [int(v) for v in t.tolist()]
+    return out
+
+
 def verify_all_rank_step_consistent(group: Optional[dist.ProcessGroup], step):
     """True iff every rank holds the same in-memory step (all-gather of step)."""
     if not group and not dist.is_initialized():

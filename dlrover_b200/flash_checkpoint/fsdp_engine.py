@@ -62,6 +62,7 @@ from ..common.constants import CheckpointConstant
 from ..common.log import default_logger as logger
 from .engine import (
     CheckpointEngine,
+    all_reduce_flags,
     check_all_rank_ready,
     timer,
     verify_all_rank_step_consistent,
@@ -197,8 +198,69 @@ def _write_memory_from_list(shm_handler=None, files=None, planner=None, blocking
     return results, no_shard, pending
 
 
+class _DeferredHostCopy:
+    """The CUDA tensors among a plan's non-sharded objects, snapshotted with one
+    device-side concatenation on the caller's stream; `get()` — called from the thread
+    that publishes the meta — brings them to the host with one copy on a side stream, so
+    the training thread never waits for a device-to-host copy."""
+
+    def __init__(self, objects: Dict[str, Any]):
+        self._objects = dict(objects)
+        self._cuda = [(k, v) for k, v in objects.items() if torch.is_tensor(v) and v.is_cuda]
+        self._flat = self._event = None
+        self._result: Optional[Dict[str, Any]] = None
+        if self._cuda:
+            self._flat = torch.cat([v.detach().contiguous().reshape(-1).view(torch.uint8)
+                                    for _, v in self._cuda])
+            self._event = torch.cuda.Event()
+            self._event.record()
+
+    def get(self) -> Dict[str, Any]:
+        if self._result is not None:
+            return self._result
+        out = self._objects
+        if self._cuda:
+            side = _copy_stream(self._flat.device)
+            with torch.cuda.stream(side):
+                side.wait_event(self._event)
+                host = self._flat.to("cpu", non_blocking=True)
+                self._flat.record_stream(side)
+            side.synchronize()
+            off = 0
+            for k, v in self._cuda:
+                n = v.numel() * v.element_size()
+                out[k] = host[off:off + n].clone().view(v.dtype).reshape(v.shape)
+                off += n
+            self._flat = None
+        self._result = out
+        return out
+
+
+_copy_streams: Dict[int, "torch.cuda.Stream"] = {}
+
+
+def _copy_stream(device) -> "torch.cuda.Stream":
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    s = _copy_streams.get(idx)
+    if s is None:
+        s = _copy_streams[idx] = torch.cuda.Stream(device=idx)
+    return s
+
+
 class SharedMemoryWriter(StorageWriter):
-    """DCP StorageWriter whose storage is the shared-memory segment."""
+    """DCP StorageWriter whose storage is the shared-memory segment.
+
+    Beyond the reference's writer (fsdp_engine.py:158-232):
+      * `announce` (set by the engine) publishes "segment is being written" — inline when
+        host tensors are among the items, else from the completion thread with the drain
+        held until it is out (see SharedMemoryHandler.write_ranges);
+      * the non-sharded objects of the LOCAL plan (before torch dedups replicated entries
+        over the ranks) are kept per rank: replicated means every rank has them, so no
+        rank needs another rank's copy to restore from its own memory
+        (the reference broadcasts rank 0's, fsdp_engine.py:512-520);
+      * last_plan / last_results let the engine reuse the plan when the structure of the
+        state dict has not changed (no DCP collective at all on such saves).
+    """
 
     def __init__(self, shm_handler: SharedMemoryHandler, blocking: bool = True) -> None:
         super().__init__()
@@ -207,6 +269,14 @@ class SharedMemoryWriter(StorageWriter):
         self.metadata: Dict[str, Any] = {}
         self.blocking = blocking
         self.pending = None
+        self.last_items: List[Tuple[str, WriteItem]] = []
+        self.last_plan: Optional[SavePlan] = None
+        self.last_results: List[WriteResult] = []
+        self.local_non_shard: List[WriteItem] = []
+        self.no_shard: Optional[_DeferredHostCopy] = None
+        self.announce = None   # Callable[[], None] or None
+        self.on_error = None
+        self.announced_inline = False
 
     def reset(self, checkpoint_id: Union[str, os.PathLike, None] = None) -> None:
         pass
@@ -219,6 +289,9 @@ class SharedMemoryWriter(StorageWriter):
         pass
 
     def prepare_local_plan(self, plan: SavePlan) -> SavePlan:
+        # every non-sharded entry this rank HOLDS (the global plan will leave each of
+        # them to one rank only)
+        self.local_non_shard = [it for it in plan.items if it.type != WriteItemType.SHARD]
         return plan
 
     def prepare_global_plan(self, global_plan: List[SavePlan]) -> List[SavePlan]:
@@ -229,9 +302,32 @@ class SharedMemoryWriter(StorageWriter):
         prefix: _StoragePrefix = plan.storage_data
         self.file_name = f"{prefix.prefix}0{DEFAULT_SUFFIX}"
         files = [(self.file_name, item) for item in plan.items]
-        results, no_shard, self.pending = _write_memory_from_list(
-            self.shm_handler, files, planner, blocking=self.blocking)
-        self.metadata["no_shard_data"] = no_shard
+        self.last_items = files  # the final local plan, in segment order
+        self.last_plan = plan
+        results, written_no_shard, dev, host, raw, total = _stage_items(files, planner)
+        objects = dict(written_no_shard)
+        for item in self.local_non_shard:
+            if item.index.fqn not in objects:
+                data = planner.resolve_data(item)
+                objects[item.index.fqn] = data.detach() if torch.is_tensor(data) else data
+        self.no_shard = _DeferredHostCopy(objects)
+        self.pending = None
+        self.announced_inline = False
+        announce = self.announce
+        if total > 0:
+            self.shm_handler.ensure_segment(total)
+            deferred = announce is not None and not self.blocking and bool(dev) and not host
+            if announce is not None and not deferred:
+                announce()
+                self.announced_inline = True
+            self.pending = self.shm_handler.write_ranges(
+                dev, host, raw, blocking=self.blocking, keepalive=[d for d, _, _ in dev],
+                pre_drain=announce if deferred else None, on_error=self.on_error)
+        elif announce is not None:
+            announce()
+            self.announced_inline = True
+        self.last_results = results
+        self.metadata["no_shard_data"] = objects  # (reference attribute; host copies: no_shard.get())
         fut: Future[List[WriteResult]] = Future()
         fut.set_result(results)
         return fut
@@ -447,20 +543,74 @@ class FsdpCheckpointEngine(CheckpointEngine):
         self._shm_writer = SharedMemoryWriter(shm_handler=self._shm_handler,
                                               blocking=not self._async_drain)
         self._shm_reader = SharedMemoryReader(self._shm_handler)
+        self._plan_cache: Optional[Dict[str, Any]] = None
+        self._published_meta: Dict[str, Any] = {}
+        self._meta_tree_published = False
+        self.last_save_reused_plan = False
 
     def get_saving_ranks(self):
         return None  # every rank holds a shard
 
+    # -- plan reuse ---------------------------------------------------------------------
+    @staticmethod
+    def _describe(value):
+        if torch.is_tensor(value):
+            placements = getattr(value, "placements", None)
+            if placements is not None:  # DTensor
+                local = value.to_local()
+                return ("D", tuple(value.shape), value.dtype, str(placements),
+                        tuple(local.shape), local.device.type)
+            return ("T", tuple(value.shape), value.dtype, value.device.type)
+        shards = getattr(value, "local_shards", None)
+        if callable(shards):  # ShardedTensor (FSDP1 SHARDED_STATE_DICT)
+            return ("S", tuple(value.size()), value.dtype,
+                    tuple((tuple(sh.metadata.shard_offsets), tuple(sh.metadata.shard_sizes))
+                          for sh in shards()))
+        return ("O", type(value).__name__)
+
+    def _structure_key(self, planner, cached_plan: Optional[SavePlan]):
+        """What the DCP plan of this rank depends on: the flattened names, every tensor's
+        global/local shape, dtype and placement, and the pickled size of the byte items
+        this rank writes (their offsets follow from it)."""
+        flat = planner.state_dict
+        key = [(k, self._describe(v)) for k, v in flat.items()]
+        if cached_plan is not None:
+            for item in cached_plan.items:
+                if item.type == WriteItemType.BYTE_IO:
+                    key.append((item.index.fqn, planner.resolve_data(item).getbuffer().nbytes))
+        return key
+
     @timer
     def save_to_memory(self, step, state_dict, paths: Dict[str, str]):
         """`paths["model_states"]` is the DIRECTORY of the step; the agent
-        stores this rank's segment there as "__<rank>_0.distcp"."""
+        stores this rank's segment there as "__<rank>_0.distcp".
+
+        The first save of a structure runs torch DCP's planning collectives; later saves
+        of the same structure reuse this rank's final plan and the global metadata and
+        run NO collective besides the readiness all-reduce (which carries one more int:
+        "my plan changed")."""
         if self._local_rank != self.local_shard_id:
             return False
-        pending = self._shm_handler.pending_save()
-        acquired = False if pending is not None else self._shm_lock.acquire(blocking=False)
-        all_rank_ready = check_all_rank_ready(self._saver_group, acquired)
-        if not all_rank_ready:
+        handler, writer = self._shm_handler, self._shm_writer
+        pending = handler.pending_save()
+        acquired = False if pending is not None else bool(self._shm_lock.acquire(blocking=False))
+        from torch.distributed.checkpoint.default_planner import DefaultSavePlanner
+
+        planner = DefaultSavePlanner()
+        changed = True
+        try:
+            planner.set_up_planner(state_dict=state_dict, storage_meta=None,
+                                   is_coordinator=self._rank == 0)
+            cache = self._plan_cache
+            key = self._structure_key(planner, cache["plan"] if cache else None)
+            changed = cache is None or key != cache["key"] or \
+                os.getenv("DLROVER_B200_FSDP_PLAN_CACHE", "1") == "0"
+        except Exception as e:  # planner internals moved: always take the DCP path
+            logger.warning(f"cannot fingerprint the DCP plan ({e}); planning every save")
+            key = None
+        not_ready, n_changed = all_reduce_flags(self._saver_group,
+                                                [0 if acquired else 1, 1 if changed else 0])
+        if not_ready:
             logger.info(f"Rank {self._rank} skips the save the checkpoint in CPU memory since "
                         "it is saving the latest checkpoint from the CPU memory into the "
                         "storage.")
@@ -471,30 +621,23 @@ class FsdpCheckpointEngine(CheckpointEngine):
         conf = CheckpointConfig(rank=self._rank, group_rank=self._group_rank,
                                 world_size=self._world_size, step=step)
         conf.writing_shm = True
-        try:
-            _dcp_save(state_dict, self._shm_writer)
-            # rank 0's DCP metadata and non-sharded objects go to every rank so
-            # each of them can restore from its own memory
-            shared = [self._shm_writer.metadata]
-            if dist.is_initialized():
-                dist.broadcast_object_list(shared, src=0)
-            self._shm_writer.metadata = shared[0]
-            name = CheckpointConstant.MODEL_STATES_NAME
-            conf.paths = {name: os.path.join(paths[name], self._shm_writer.file_name)}
-            meta_dict = {DLROVER_CKPT_CONFIG_KEY: conf}
-            meta_dict.update(self._shm_writer.metadata)
-            self._shm_handler.metadata.set(meta_dict)  # step visible, bytes not yet final
-        except BaseException:
-            if acquired:
-                self._shm_handler.wait_pending()
-                self._shm_lock.release()
-            raise
+        name = CheckpointConstant.MODEL_STATES_NAME
+        reuse = n_changed == 0
+        previous = dict(self._published_meta)  # what the agent holds for this shard now
 
-        def completed():
-            conf.writing_shm = False
-            self._shm_handler.metadata.set(meta_dict)
-            if acquired:
-                self._shm_lock.release()
+        def announce():
+            # before the first byte of the segment changes.  A reused plan already knows
+            # the whole meta; a new one is still being agreed on: keep the previous tree
+            # under the new step with writing_shm set
+            if reuse:
+                meta = {DLROVER_CKPT_CONFIG_KEY: conf, "dcp_metadata": cache["dcp_metadata"],
+                        "no_shard_data": writer.no_shard.get()}
+                handler.metadata.next_unchanged = self._meta_tree_published
+            else:
+                meta = {**previous, DLROVER_CKPT_CONFIG_KEY: conf}
+                handler.metadata.next_unchanged = bool(previous) and self._meta_tree_published
+            handler.metadata.payload_bytes = handler._buffer_size
+            handler.metadata.set(meta)
 
         def failed():
             # the segment is torn: the meta keeps writing_shm=True (the agent and a
@@ -502,7 +645,62 @@ class FsdpCheckpointEngine(CheckpointEngine):
             if acquired:
                 self._shm_lock.release()
 
-        drain = self._shm_writer.pending
+        writer.announce, writer.on_error = announce, failed
+        try:
+            conf.paths = {name: os.path.join(paths[name], f"__{self._rank}_0{DEFAULT_SUFFIX}")}
+            if reuse:
+                writer.write_data(cache["plan"], planner)
+                if [(r.index, r.size_in_bytes) for r in writer.last_results] != cache["results"]:
+                    raise RuntimeError("reused DCP plan produced different item sizes")
+                dcp_metadata = cache["dcp_metadata"]
+            else:
+                if hasattr(dist_cp, "save"):
+                    dist_cp.save(state_dict, storage_writer=writer, planner=planner)
+                else:
+                    dist_cp.save_state_dict(state_dict=state_dict, storage_writer=writer,
+                                            planner=planner)
+                # the coordinator's global metadata goes to every rank
+                shared = [writer.metadata.get("dcp_metadata")]
+                if dist.is_initialized():
+                    dist.broadcast_object_list(shared, src=0)
+                dcp_metadata = shared[0]
+                self._plan_cache = None
+                if key is not None and writer.last_plan is not None:
+                    # the byte-item sizes belong to the key the NEXT save is compared with
+                    self._plan_cache = {
+                        "plan": writer.last_plan, "dcp_metadata": dcp_metadata,
+                        "results": [(r.index, r.size_in_bytes) for r in writer.last_results],
+                        "key": self._structure_key(planner, writer.last_plan)}
+            conf.paths = {name: os.path.join(paths[name], writer.file_name)}
+        except BaseException:
+            writer.announce = writer.on_error = None
+            if acquired:
+                try:
+                    handler.wait_pending()
+                except BaseException:
+                    pass
+                if self._shm_lock.locked():
+                    self._shm_lock.release()
+            raise
+        writer.announce = writer.on_error = None
+        self.last_save_reused_plan = reuse
+        no_shard = writer.no_shard
+
+        def completed():
+            conf.writing_shm = False
+            meta = {DLROVER_CKPT_CONFIG_KEY: conf, "dcp_metadata": dcp_metadata,
+                    "no_shard_data": no_shard.get()}
+            # only the header flips when the announcement already carried this tree
+            handler.metadata.next_unchanged = reuse and self._meta_tree_published
+            handler.metadata.payload_bytes = handler._buffer_size
+            handler.metadata.set(meta)
+            self._published_meta = {"dcp_metadata": dcp_metadata,
+                                    "no_shard_data": meta["no_shard_data"]}
+            self._meta_tree_published = True
+            if acquired:
+                self._shm_lock.release()
+
+        drain = writer.pending
         if drain is None or drain.done():
             try:
                 if drain is not None:
@@ -519,14 +717,26 @@ class FsdpCheckpointEngine(CheckpointEngine):
                     drain.wait()
                 except BaseException as e:
                     logger.error(f"FSDP shard drain of step {conf.step} failed: {e}")
+                    return  # write_ranges' on_error (= failed) already ran
+                try:
+                    completed()
+                except BaseException as e:
+                    logger.error(f"publishing step {conf.step} failed: {e}", exc_info=True)
                     failed()
-                    return
-                completed()
 
-            threading.Thread(target=waiter, name="fc-fsdp-drain", daemon=True).start()
-            self._finalizer = waiter
+            t = threading.Thread(target=waiter, name="fc-fsdp-drain", daemon=True)
+            t.start()
+            self._finalizer = t
         self._cached_step = conf.step
         return True
+
+    def wait_memory_save(self, timeout: Optional[float] = None) -> bool:
+        ok = super().wait_memory_save(timeout)
+        t = getattr(self, "_finalizer", None)
+        if ok and t is not None:
+            t.join(timeout)
+            ok = not t.is_alive()
+        return ok
 
     def save_to_storage(self, step, state_dict, paths: Dict[str, str]):
         success = True

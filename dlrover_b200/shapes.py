@@ -129,3 +129,84 @@ def payload_bytes(sd) -> int:
         elif torch.is_tensor(v):
             total += v.numel() * v.element_size()
     return total
+
+
+class ShardedStateFactory:
+    """BASELINE configs[2] without the model code: the state an FSDP full-shard job hands
+    to the checkpointer — every parameter row-sharded over the ranks (DTensor, Shard(0)),
+    its AdamW moments sharded the same way (fp32), a replicated `step` per parameter and
+    the non-tensor param_groups.  FSDP gives out FRESH tensors on every state_dict() call;
+    `build(variant)` reproduces that: the local shards of variant 0 and 1 are views of
+    the same flat buffers at different byte offsets, so every device pointer changes from
+    one save to the next while the memory footprint stays that of one state."""
+
+    SHIFT = 512  # bytes between the two variants' views
+
+    def __init__(self, shapes, world: int, rank: int, device, mesh=None, with_optimizer=True,
+                 weight_dtype=torch.bfloat16, seed=4321):
+        self.world, self.rank, self.device, self.mesh = world, rank, device, mesh
+        self.with_optimizer = with_optimizer
+        self.weight_dtype = weight_dtype
+        self.full_shapes = list(shapes)
+        self.local_shapes = shard_shapes(self.full_shapes, world, rank)
+        w_elems = sum(int(torch.Size(s).numel()) for _, s in self.local_shapes)
+        w_es = torch.empty(0, dtype=weight_dtype).element_size()
+        self._wbuf = torch.empty(w_elems * w_es + self.SHIFT, dtype=torch.uint8, device=device)
+        fill_(self._wbuf, seed + rank)
+        self._mbuf = None
+        if with_optimizer:
+            self._mbuf = torch.empty(2 * w_elems * 4 + self.SHIFT, dtype=torch.uint8, device=device)
+            fill_(self._mbuf, seed + 100 + rank)
+        self.local_bytes = w_elems * w_es + (2 * w_elems * 4 if with_optimizer else 0)
+
+    def _wrap(self, local, full_shape):
+        if self.mesh is None:
+            return local
+        from torch.distributed.tensor import DTensor, Shard
+
+        stride = [1] * len(full_shape)
+        for d in range(len(full_shape) - 2, -1, -1):
+            stride[d] = stride[d + 1] * full_shape[d + 1]
+        return DTensor.from_local(local, self.mesh, [Shard(0)], run_check=False,
+                                  shape=torch.Size(full_shape), stride=tuple(stride))
+
+    def build(self, variant: int):
+        """{"model": {...}, "optim": {"state": {...}, "param_groups": [...]}} of this rank."""
+        shift = self.SHIFT * (variant & 1)
+        w_es = torch.empty(0, dtype=self.weight_dtype).element_size()
+        model, opt_state = OrderedDict(), OrderedDict()
+        wo, mo = shift, shift
+        for (name, full), (_, loc) in zip(self.full_shapes, self.local_shapes):
+            n = int(torch.Size(loc).numel())
+            w = self._wbuf[wo:wo + n * w_es].view(self.weight_dtype).view(loc)
+            wo += n * w_es
+            model[name] = self._wrap(w, full)
+            if self.with_optimizer:
+                m1 = self._mbuf[mo:mo + n * 4].view(torch.float32).view(loc)
+                m2 = self._mbuf[mo + n * 4:mo + 2 * n * 4].view(torch.float32).view(loc)
+                mo += 2 * n * 4
+                opt_state[name] = {"step": torch.tensor(float(1 + variant), device=self.device),
+                                   "exp_avg": self._wrap(m1, full),
+                                   "exp_avg_sq": self._wrap(m2, full)}
+        sd = {"model": model}
+        if self.with_optimizer:
+            sd["optim"] = {"state": opt_state,
+                           "param_groups": [{"lr": 3e-4, "betas": (0.9, 0.95), "eps": 1e-8,
+                                             "weight_decay": 0.1,
+                                             "params": [n for n, _ in self.full_shapes]}]}
+        return sd
+
+    @staticmethod
+    def local_tensors(sd):
+        """fqn -> the local (plain) tensor behind every sharded leaf of build()'s result."""
+        out = OrderedDict()
+
+        def local(t):
+            return t.to_local() if hasattr(t, "to_local") else t
+
+        for k, v in sd["model"].items():
+            out[f"model.{k}"] = local(v)
+        for k, st in sd.get("optim", {}).get("state", {}).items():
+            out[f"optim.state.{k}.exp_avg"] = local(st["exp_avg"])
+            out[f"optim.state.{k}.exp_avg_sq"] = local(st["exp_avg_sq"])
+        return out

@@ -623,6 +623,10 @@ class _MetaPlane:
             self._ctl_looked = True
         return self._ctl
 
+    # keys whose values change at every save: they travel in the small per-save blob
+    # next to the CheckpointConfig instead of forcing the big tree to be re-pickled
+    VOLATILE_KEYS = ("no_shard_data",)
+
     def set(self, meta_dict):
         unchanged, self.next_unchanged = self.next_unchanged, False
         ctl = self.ctl
@@ -634,14 +638,24 @@ class _MetaPlane:
                 self.dict._dict = {}
                 return
             conf = meta_dict.get(DLROVER_CKPT_CONFIG_KEY)
+            volatile = {DLROVER_CKPT_CONFIG_KEY: conf}
+            for k in self.VOLATILE_KEYS:
+                if k in meta_dict:
+                    volatile[k] = meta_dict[k]
+            small = pickle.dumps(volatile, protocol=pickle.HIGHEST_PROTOCOL)
+            in_small = set(volatile)
+            if len(small) > ctl.conf_capacity:
+                in_small = {DLROVER_CKPT_CONFIG_KEY}
+                small = pickle.dumps({DLROVER_CKPT_CONFIG_KEY: conf},
+                                     protocol=pickle.HIGHEST_PROTOCOL)
+                unchanged = False  # the volatile objects ride in the big blob this time
             blob = None
             if not unchanged or not ctl.has_meta():
-                rest = {k: v for k, v in meta_dict.items() if k != DLROVER_CKPT_CONFIG_KEY}
+                rest = {k: v for k, v in meta_dict.items() if k not in in_small}
                 blob = pickle.dumps(rest, protocol=pickle.HIGHEST_PROTOCOL)
             ok = ctl.publish(step=int(getattr(conf, "step", 0) or 0),
                              writing=bool(getattr(conf, "writing_shm", False)),
-                             payload_bytes=int(self.payload_bytes),
-                             conf_blob=pickle.dumps(conf, protocol=pickle.HIGHEST_PROTOCOL),
+                             payload_bytes=int(self.payload_bytes), conf_blob=small,
                              meta_blob=blob)
             if ok:
                 self.ctl_publishes += 1
@@ -661,7 +675,9 @@ class _MetaPlane:
             if snap is not None:
                 _step, _writing, _payload, conf_blob, _gen, rest = snap
                 out = dict(rest)
-                conf = pickle.loads(conf_blob) if conf_blob else None
+                volatile = pickle.loads(conf_blob) if conf_blob else {}
+                conf = volatile.pop(DLROVER_CKPT_CONFIG_KEY, None)
+                out.update(volatile)
                 if conf is not None:
                     out[DLROVER_CKPT_CONFIG_KEY] = conf
                 return out
@@ -874,9 +890,25 @@ class SharedMemoryHandler:
         ranks); raw chunks are written as given (hand them to one rank only).
         """
         keepalive = keepalive if keepalive is not None else []
-        for chunk, off in raw_chunks:
-            view = memoryview(chunk).cast("B")
-            self.shared_memory.buf[off:off + view.nbytes] = view
+
+        def write_raw():
+            for chunk, off in raw_chunks:
+                view = memoryview(chunk).cast("B")
+                self.shared_memory.buf[off:off + view.nbytes] = view
+
+        # With a deferred announcement (pre_drain) nothing may touch the segment before
+        # it is out: immutable byte chunks are then written right after it, wherever it
+        # runs.  Host TENSORS are copied now (the caller announces first in that case:
+        # the training thread may change them as soon as this call returns).
+        raw_deferred = pre_drain is not None and bool(raw_chunks) and not host_ranges
+        if raw_deferred:
+            announce_only = pre_drain
+
+            def pre_drain():  # noqa: F811
+                announce_only()
+                write_raw()
+        else:
+            write_raw()
         if host_ranges:
             keep, ptrs, offs, lens = [], [], [], []
             for t, off, nbytes in host_ranges:

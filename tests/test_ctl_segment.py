@@ -22,7 +22,7 @@ def test_publish_snapshot_and_generations(run_env):
         peer = cs.ControlSegment.attach(3)
         assert peer is not None and peer.snapshot() is None and not peer.has_meta()
         tree = {"model": {"w": ("meta", 1, 2)}, "lr": 0.1}
-        conf = pickle.dumps({"step": 5})
+        conf = pickle.dumps({"step": 5})  # any small blob
         assert peer.publish(step=5, writing=True, payload_bytes=99, conf_blob=conf,
                             meta_blob=pickle.dumps(tree))
         step, writing, payload, conf_blob, gen, meta = owner.snapshot()
