@@ -76,8 +76,14 @@ def _parallel_write(path: str, view: memoryview, threads: int, piece: int = 64 <
     releases the GIL); same bytes, same file, fsync'd once at the end."""
     from concurrent.futures import ThreadPoolExecutor
 
+    from . import direct_io
+
     view = view.cast("B")
     total = view.nbytes
+    if direct_io.enabled_for(path):
+        # block-device backed directory: whole 4 KiB blocks bypass the page cache
+        direct_io.write_buffer(path, view, threads)
+        return
     fd = os.open(path, os.O_WRONLY | os.O_CREAT | os.O_TRUNC, 0o644)
     try:
         os.ftruncate(fd, total)

@@ -202,6 +202,27 @@ def fast_save(obj, path: str, threads: int = 4, pickle_protocol: int = 2) -> Non
         total = cd_offset + len(cd) + len(end)
 
         # ---- write ----------------------------------------------------------------
+        from .common import direct_io
+
+        if direct_io.enabled_for(path):
+            # block-device backed directory: the whole 4 KiB blocks inside each record's
+            # payload go through O_DIRECT (page-aligned bounce buffers), headers and
+            # partial blocks through the page cache — same bytes at the same offsets
+            w = direct_io.DirectWriter(path, total, threads)
+            try:
+                for (name, view, size), (nm, crc, _, lfh_off, data_off, lfh, dd) in zip(
+                        records, entries):
+                    w.write_small(lfh, lfh_off)
+                    if dd:
+                        w.write_small(dd, data_off + size)
+                    if size:
+                        w.add(view, data_off)
+                w.write_small(bytes(cd) + end, cd_offset)
+                w.run()
+            finally:
+                w.close(sync=False)
+            del rec
+            return
         fd = os.open(path, os.O_WRONLY | os.O_CREAT | os.O_TRUNC, 0o644)
         try:
             os.ftruncate(fd, total)

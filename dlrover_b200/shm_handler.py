@@ -723,6 +723,7 @@ class SharedMemoryHandler:
         self._need_creation = True
         self._announced_once = False
         self._meta_published = False  # the last save's meta tree reached the meta plane
+        self._completion_queue = None
         self._layout: Optional[_Layout] = None  # of the previous save (TensorMeta reuse)
         self._stager: Optional[_DeviceStager] = None
         self._pending: Optional[PendingSave] = None
@@ -753,6 +754,9 @@ class SharedMemoryHandler:
             self.wait_pending()
         except BaseException as e:  # already logged by the completion thread
             logger.warning(f"closing after a failed drain: {e}")
+        if self._completion_queue is not None:
+            self._completion_queue.put(None)
+            self._completion_queue = None
         if self._stager is not None:
             self._stager.close()
             self._stager = None
@@ -1009,9 +1013,32 @@ class SharedMemoryHandler:
             self._pending = None
             pending.wait()  # re-raise a drain error
             return None
-        threading.Thread(target=self._run_completion, args=(pending,), name="fc-drain",
-                         daemon=True).start()
+        self._completion_worker().put(pending)
         return pending
+
+    def _completion_worker(self):
+        """One long-lived thread per handler finishes the non-blocking saves in order
+        (starting a thread per save costs the training thread ~0.1 ms)."""
+        q = self._completion_queue
+        if q is None:
+            import queue
+
+            q = self._completion_queue = queue.SimpleQueue()
+            ref = weakref.ref(self)
+
+            def loop():
+                while True:
+                    pending = q.get()
+                    if pending is None:
+                        return
+                    handler = ref()
+                    pending._complete()
+                    if handler is not None:
+                        handler.last_timings = pending.timings
+                    del handler
+
+            threading.Thread(target=loop, name="fc-drain", daemon=True).start()
+        return q
 
     MIN_SNAPSHOT_BYTES = 64 << 20  # below this a snapshot part is not worth a kernel
 

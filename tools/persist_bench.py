@@ -35,6 +35,7 @@ for root in ("/dev/shm", "/tmp"):
     t1 = time.time()
     res = {"root": root, "bytes": S, "cores": os.cpu_count(),
            "torch_save_s": round(t1 - t0, 2), "torch_save_GBps": round(S / (t1 - t0) / 1e9, 2)}
+    os.environ["DLROVER_B200_DIRECT_IO"] = "0"
     for th in (4, 16, 32):
         t0 = time.time()
         fast_save(sd, d + "/b/rank_0.pt", threads=th)
@@ -42,6 +43,27 @@ for root in ("/dev/shm", "/tmp"):
         res[f"fast_{th}t_s"] = round(dt, 2)
         res[f"fast_{th}t_GBps"] = round(S / dt / 1e9, 2)
     res["identical"] = sha(d + "/a/rank_0.pt") == sha(d + "/b/rank_0.pt")
+    # O_DIRECT (second half): only meaningful on a block-device backed fs
+    from dlrover_b200.common import direct_io
+    os.environ["DLROVER_B200_DIRECT_IO"] = "1"
+    res["fs_type"] = direct_io._fs_type(d)
+    res["o_direct_usable"] = direct_io.enabled_for(d + "/b/rank_0.pt")
+    if res["o_direct_usable"] and root != "/dev/shm":
+        for th in (4, 16):
+            t0 = time.time()
+            fast_save(sd, d + "/b/rank_0.pt", threads=th)
+            os.sync()
+            dt = time.time() - t0
+            res[f"direct_{th}t_incl_sync_s"] = round(dt, 2)
+            res[f"direct_{th}t_GBps"] = round(S / dt / 1e9, 2)
+        res["direct_identical"] = sha(d + "/a/rank_0.pt") == sha(d + "/b/rank_0.pt")
+        os.environ["DLROVER_B200_DIRECT_IO"] = "0"
+        t0 = time.time()
+        fast_save(sd, d + "/b/rank_0.pt", threads=16)
+        os.sync()
+        dt = time.time() - t0
+        res["buffered_16t_incl_sync_s"] = round(dt, 2)
+        res["buffered_16t_incl_sync_GBps"] = round(S / dt / 1e9, 2)
     print(json.dumps(res), flush=True)
     os.remove(d + "/a/rank_0.pt")
     os.remove(d + "/b/rank_0.pt")
