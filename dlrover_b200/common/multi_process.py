@@ -539,6 +539,7 @@ class SharedMemory:
         flags = os.O_RDWR | ((os.O_CREAT | os.O_EXCL) if create else 0)
         self._fd = -1
         self._mmap: Optional[mmap.mmap] = None
+        self._dma_mmap: Optional[mmap.mmap] = None
         self._buf: Optional[memoryview] = None
         if name is None:
             while True:
@@ -577,8 +578,20 @@ class SharedMemory:
 
     @property
     def address(self) -> int:
-        """Virtual address of byte 0 (for cudaHostRegister / DMA targets)."""
+        """Virtual address of byte 0 of the mapping `buf` views."""
         return ctypes.addressof(ctypes.c_char.from_buffer(self._mmap))
+
+    @property
+    def dma_address(self) -> int:
+        """Virtual address of byte 0 of a SECOND mapping of the same object, used only as
+        the DMA target that gets page-locked (cudaHostRegister, slice by slice).  CUDA
+        looks at the address to decide whether host memory is pinned, and a copy that
+        straddles two registered slices fails — tensors handed to the user view `buf`,
+        which stays ordinary pageable memory as far as CUDA is concerned (a
+        `param.copy_(view)` then behaves exactly like with the reference)."""
+        if self._dma_mmap is None:
+            self._dma_mmap = mmap.mmap(self._fd, self._size)
+        return ctypes.addressof(ctypes.c_char.from_buffer(self._dma_mmap))
 
     def stale(self) -> bool:
         """True when the NAME no longer refers to the object this mapping came from
@@ -606,6 +619,12 @@ class SharedMemory:
             except BufferError:
                 pass
             self._mmap = None
+        if self._dma_mmap is not None:
+            try:
+                self._dma_mmap.close()
+            except BufferError:
+                pass
+            self._dma_mmap = None
         if self._fd >= 0:
             os.close(self._fd)
             self._fd = -1

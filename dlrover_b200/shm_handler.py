@@ -372,7 +372,7 @@ class _DeviceStager:
         writes them first), pinning inline for small windows, else in the background
         after the first transfer (pin_in_background)."""
         hi = shm.size if hi is None else hi
-        window = (shm.address + lo, hi - lo)
+        window = (shm.dma_address + lo, hi - lo)
         if window == self._attached:
             return
         self.detach()
@@ -943,7 +943,7 @@ class SharedMemoryHandler:
         if prepared is not None:
             lo, hi = window if window is not None else (0, self.shared_memory.size)
             stager.attach(self.shared_memory, lo, hi)
-            host_addr = self.shared_memory.address + lo
+            host_addr = self.shared_memory.dma_address + lo
             current = torch.cuda.current_stream(stager.device_index)
             if stream is None:
                 stream = current
@@ -1358,7 +1358,7 @@ class SharedMemoryHandler:
             direct = True
         staged = not stager.pinned()  # e.g. a restarted trainer: bounce slots, no 16 GB pin
         t0 = time.perf_counter()
-        plan.restore_async(self.shared_memory.address, stream, direct=direct)
+        plan.restore_async(self.shared_memory.dma_address, stream, direct=direct)
         stager.ctx.restore_wait()
         wall_ms = (time.perf_counter() - t0) * 1e3
         fill, scatter, _ = stager.ctx.restore_timings()

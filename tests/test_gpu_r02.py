@@ -278,3 +278,28 @@ def test_property_device_path_matches_oracle(cuda_device, run_env, sd):
     finally:
         handler.unlink()
         handler.close()
+
+
+def test_user_views_stay_usable_while_the_dma_mapping_is_pinned_in_slices(cuda_device, run_env):
+    """The segment is pinned slice by slice through a SECOND mapping; the tensors
+    load_state_dict() hands out view the first one, so a plain `param.copy_(view)` of a
+    tensor that straddles two slices works (it failed with "invalid argument" when the
+    views were on the sliced registration)."""
+    sd = {"a": torch.arange(50 << 20, dtype=torch.int32, device="cuda"),      # 200 MiB
+          "b": torch.arange(50 << 20, dtype=torch.int32, device="cuda") * 3}  # straddles 256 MiB
+    handler = SharedMemoryHandler(0, host=True)
+    try:
+        full = dict(sd)
+        full[DLROVER_CKPT_CONFIG_KEY] = CheckpointConfig(step=1, paths={})
+        handler.save_state_dict(full)                 # first save: bounce slots
+        assert handler.wait_segment_pinned(60)        # pinned in the background since
+        handler.save_state_dict(full)                 # plain DMA now
+        views = handler.load_state_dict()
+        for k in ("a", "b"):
+            target = torch.zeros_like(sd[k])
+            target.copy_(views[k])                    # the reference's restore idiom
+            assert torch.equal(target, sd[k])
+        del views
+    finally:
+        handler.unlink()
+        handler.close()
