@@ -548,7 +548,29 @@ def measure_cooperative(args, sd, S, world, dev):
         off += n
     ok = bool(sum_over_ranks(0.0 if ok else 1.0, world, dev) == 0)
     del img
+    # cooperative restore: every rank needs the WHOLE image back; each reads 1/N of it from
+    # host memory and the slices are all-gathered between the arenas over NVLink
+    keys = list(sd)
+    probe = [sd[k].clone() for k in (keys[0], keys[len(keys) // 2], keys[-1])]
+    restores = []
+    for _ in range(3):
+        for t in sd.values():
+            t.zero_()
+        barrier_sync(world)
+        t0 = time.perf_counter()
+        step_back = ckpt.load_checkpoint_into(sd)
+        torch.cuda.synchronize()
+        restores.append(max_over_ranks(time.perf_counter() - t0, world, dev))
+    restored_ok = step_back > 0 and all(
+        torch.equal(sd[k], p) for k, p in zip((keys[0], keys[len(keys) // 2], keys[-1]), probe))
+    restored_ok = bool(sum_over_ranks(0.0 if restored_ok else 1.0, world, dev) == 0)
+    restore_stats = dict(ckpt.engine._shm_handler.last_restore_stats)
     out = {"value": S * args.steps / dt / 1e9, "unit": UNIT,
+           "restore": {"ms": min(restores) * 1e3, "first_ms": restores[0] * 1e3,
+                       "GBps_per_rank": S / min(restores) / 1e9,
+                       "what": "load_checkpoint_into on every rank at once: each rank gets the "
+                               "whole image back (slowest rank's wall time)",
+                       "bit_exact_spot_check": restored_ok, "device_times": restore_stats},
            "what": f"ONE {S / 1e9:.2f} GB image (replicated state) per node, {world} ranks each "
                    "gather + drain 1/N of it into the same segment; value = image bytes / wall "
                    "time of save_checkpoint(MEMORY)+wait_memory_save (slowest rank)",

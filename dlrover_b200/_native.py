@@ -99,6 +99,7 @@ _SIGNATURES = {
         [_vp, _u32, ctypes.POINTER(_vp), ctypes.POINTER(_u64), ctypes.POINTER(_u64), ctypes.c_int],
     ),
     "fc_restore_async": (ctypes.c_int, [_vp, _vp, _vp]),
+    "fc_arena_fill": (ctypes.c_int, [_vp, _vp, _u64, _u64, _vp]),
     "fc_restore_wait": (ctypes.c_int, [_vp]),
     "fc_restore_timings": (ctypes.c_int, [_vp, _fp, _fp, _fp]),
 }
@@ -424,6 +425,25 @@ class Context:
             "fc_save_timings",
         )
         return a.value, b.value, c.value
+
+    def arena_fill(self, host_ptr: int, lo: int, hi: int, stream=None):
+        """Host bytes [lo, hi) -> arena bytes [lo, hi); `stream` waits for them."""
+        _check(load_library().fc_arena_fill(self.handle, host_ptr, int(lo), int(hi),
+                                            _stream_ptr(stream)), "fc_arena_fill")
+
+    def arena_tensor(self, nbytes: int):
+        """The first nbytes of the arena as a uint8 torch tensor (no copy)."""
+        import torch
+
+        ptr, size = self.arena_info()
+        if nbytes > size:
+            raise NativeError(FC_EINVAL, "arena_tensor", "arena smaller than requested")
+
+        class _Arena:
+            __cuda_array_interface__ = {"shape": (int(nbytes),), "typestr": "|u1",
+                                        "data": (ptr, False), "version": 2}
+
+        return torch.as_tensor(_Arena(), device=torch.device("cuda", self.device))
 
     def restore_wait(self):
         _check(load_library().fc_restore_wait(self.handle), "fc_restore_wait")

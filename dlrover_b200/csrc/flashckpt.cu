@@ -1905,6 +1905,43 @@ extern "C" int fc_restore_async(fc_plan* p, const void* host_base, void* stream)
   return FC_OK;
 }
 
+extern "C" int fc_arena_fill(fc_ctx* c, const void* host_base, uint64_t lo, uint64_t hi,
+                             void* stream) {
+  if (!c || !host_base || hi < lo) return fail(FC_EINVAL, "fc_arena_fill: bad argument%s%s");
+  FC_GUARD(c);
+  int rc = refresh_inflight(c);
+  if (rc) return rc;
+  if (c->save_inflight || c->restore_inflight)
+    return fail(FC_EBUSY, "fc_arena_fill: arena busy%s%s");
+  if (hi > c->arena_bytes) return fail(FC_EINVAL, "fc_arena_fill: arena too small%s%s");
+  if (hi == lo) return FC_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  const uint8_t* hb = static_cast<const uint8_t*>(host_base);
+  // whatever `stream` still does with the arena must be over first
+  FC_CUDA(cudaEventRecord(c->ev_scatter_end, s));
+  FC_CUDA(cudaStreamWaitEvent(c->copy_stream, c->ev_scatter_end, 0));
+  FC_CUDA(cudaEventRecord(c->ev_fill_start, c->copy_stream));
+  const int staged = staged_threads_for(c, hb + lo, hi - lo);
+  if (staged > 0) {
+    std::vector<StagePiece> pieces;
+    stage_pieces(pieces, c->arena + lo, const_cast<uint8_t*>(hb) + lo, hi - lo, c->stage_slot);
+    cudaError_t e = stage_run(c, pieces, false, c->ev_scatter_end, staged);
+    if (e != cudaSuccess) return fail(FC_ECUDA, "fc_arena_fill (staged): %s", cudaGetErrorString(e));
+    c->n_memcpys += pieces.size();
+    FC_CUDA(cudaEventRecord(c->ev_fill_end, c->copy_stream));
+  } else {
+    const SliceClip clip(c, hb + lo);
+    for (uint64_t o = lo, len = 0; o < hi; o += len) {
+      len = clip(hb + o, std::min<uint64_t>(kDmaPiece, hi - o));
+      FC_CUDA(cudaMemcpyAsync(c->arena + o, hb + o, len, cudaMemcpyHostToDevice, c->copy_stream));
+      c->n_memcpys += 1;
+    }
+    FC_CUDA(cudaEventRecord(c->ev_fill_end, c->copy_stream));
+    FC_CUDA(cudaStreamWaitEvent(s, c->ev_fill_end, 0));
+  }
+  return FC_OK;
+}
+
 extern "C" int fc_restore_wait(fc_ctx* c) {
   if (!c) return fail(FC_EINVAL, "fc_restore_wait: null ctx%s%s");
   FC_GUARD(c);

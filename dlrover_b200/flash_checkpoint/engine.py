@@ -340,6 +340,18 @@ class CheckpointEngine(metaclass=ABCMeta):
         if self._coop_wanted and backend != default_backend:
             # the cooperative save's readiness check spans ALL ranks
             self._coop_group = dist.new_group(backend=backend, timeout=timedelta(seconds=60))
+        self._node_group = None  # NCCL group of this node's ranks (cooperative restore)
+        self._node_group_ok = False
+        if self._coop_wanted and default_backend == "nccl":
+            local_world = env_utils.get_local_world_size()
+            if self._world_size == local_world:
+                self._node_group_ok = True  # the default group IS the node
+            elif self._world_size % local_world == 0:
+                for node in range(self._world_size // local_world):
+                    ranks = list(range(node * local_world, (node + 1) * local_world))
+                    g = dist.new_group(ranks=ranks, backend="nccl", timeout=timedelta(seconds=120))
+                    if self._rank in ranks:
+                        self._node_group, self._node_group_ok = g, True
         everyone_saves = self._saving_ranks is None or len(self._saving_ranks) == self._world_size
         if backend == default_backend and everyone_saves:
             if self._local_rank == 0:
@@ -639,8 +651,14 @@ class CheckpointEngine(metaclass=ABCMeta):
         passed = verify_all_rank_step_consistent(self._loader_group, config.step)
         if not passed or config.step <= 0:
             return 0, {}
+        coop = None
+        if self._coop_wanted and self._node_group_ok and \
+                os.getenv("DLROVER_B200_COOP_RESTORE", "1") not in ("0", "false", "False"):
+            # replicated state, every local rank restores: each reads 1/n from host memory,
+            # the slices travel between the GPUs over NVLink
+            coop = (self._local_rank, env_utils.get_local_world_size(), self._node_group)
         stats = self._shm_handler.restore_into(target_state_dict, stream=stream, strict=strict,
-                                               pin_after=not self._coop_wanted)
+                                               pin_after=not self._coop_wanted, coop=coop)
         return config.step, stats
 
     def _restore_memory_from_replica(self):

@@ -1265,7 +1265,7 @@ class SharedMemoryHandler:
         return state_dict
 
     def restore_into(self, target, stream=None, strict: bool = True,
-                     pin_after: bool = True) -> Dict[str, float]:
+                     pin_after: bool = True, coop=None) -> Dict[str, float]:
         """Scatter the in-memory checkpoint straight into the live tensors of
         `target` (same tree structure as what was saved; extra keys on either
         side raise when strict).  CUDA leaves: one DMA fill of the arena + one
@@ -1274,7 +1274,12 @@ class SharedMemoryHandler:
 
         Replaces `sd = load_state_dict(); model.load_state_dict(sd)` (per
         parameter H2D copies from pageable memory, reference ckpt_saver.py:
-        144-161 + user code)."""
+        144-161 + user code).
+
+        coop=(index, n, process_group): a REPLICATED state that all n local ranks
+        restore at the same time — each rank reads only 1/n of the image from host
+        memory into its arena and the slices are exchanged over NVLink (NCCL
+        all-gather, in place) before the scatter kernel; every rank must call."""
         self.wait_pending()
         meta_dict = self.metadata.get()
         config = meta_dict.get(DLROVER_CKPT_CONFIG_KEY, CheckpointConfig())
@@ -1340,8 +1345,41 @@ class SharedMemoryHandler:
                 if stream is None:
                     stream = torch.cuda.current_stream(stager.device_index)
                 plan = stager.plan_for(prepared, role="restore", stream=stream)
-                stats.update(self._run_restore(stager, plan, stream, pin_after=pin_after))
+                if coop is not None:
+                    stats.update(self._run_restore_cooperative(stager, plan, stream, coop))
+                else:
+                    stats.update(self._run_restore(stager, plan, stream, pin_after=pin_after))
         return stats
+
+    def _run_restore_cooperative(self, stager: _DeviceStager, plan, stream, coop):
+        """Each of the n local ranks fills 1/n of its arena from the segment (its own PCIe
+        link), NCCL all-gathers the slices in place over NVLink, one scatter kernel."""
+        import torch.distributed as dist
+
+        index, n, group = coop
+        total = self.shared_memory.size
+        align = CoopContext.ALIGN
+        w = (total + n * align - 1) // (n * align) * align   # equal slices (NCCL wants them equal)
+        stager.ctx.arena_reserve(n * w)
+        lo, hi = min(total, index * w), min(total, (index + 1) * w)
+        t0 = time.perf_counter()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        with torch.cuda.stream(stream):
+            ev[0].record(stream)
+            stager.ctx.arena_fill(self.shared_memory.dma_address, lo, hi, stream)
+            ev[1].record(stream)
+            arena = stager.ctx.arena_tensor(n * w)
+            dist.all_gather_into_tensor(arena, arena[index * w:(index + 1) * w], group=group)
+            ev[2].record(stream)
+            plan.unpack(stream)
+            ev[3].record(stream)
+        ev[3].synchronize()
+        self.last_restore_stats = {
+            "device_bytes": float(plan.payload_bytes), "fill_ms": ev[0].elapsed_time(ev[1]),
+            "allgather_ms": ev[1].elapsed_time(ev[2]), "scatter_ms": ev[2].elapsed_time(ev[3]),
+            "cooperative": float(n), "slice_bytes": float(hi - lo),
+            "wall_ms": (time.perf_counter() - t0) * 1e3, "staged": float(not stager.pinned())}
+        return dict(self.last_restore_stats)
 
     DIRECT_RESTORE_MIN_SPAN = 1 << 20  # average span size from which in-place restore wins
 

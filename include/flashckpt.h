@@ -271,6 +271,15 @@ int fc_restore_async(fc_plan* plan, const void* host_base, void* stream);
  * few large spans or when HBM has no room for the arena; fc_restore_wait /
  * fc_restore_timings apply (scatter time = 0). */
 int fc_restore_direct_async(fc_plan* plan, const void* host_base, void* stream);
+/* Cooperative restore of a REPLICATED state (every local rank needs the whole image):
+ * fill only the arena bytes [lo, hi) from host_base+[lo, hi) (plain DMA when the range
+ * is page-locked, bounce slots when it is not — then the call returns with the data on
+ * the device), `stream` waits for it.  The caller exchanges the slices between the local
+ * ranks' arenas over NVLink (NCCL all-gather, in place) and scatters with
+ * fc_unpack_async: each rank reads 1/n of the image from host memory instead of all of
+ * it (the reference: every rank copies every tensor from shared memory itself,
+ * ckpt_saver.py:144-161 + load_state_dict). */
+int fc_arena_fill(fc_ctx* ctx, const void* host_base, uint64_t lo, uint64_t hi, void* stream);
 int fc_restore_wait(fc_ctx* ctx);
 int fc_restore_timings(fc_ctx* ctx, float* fill_ms, float* scatter_ms, float* total_ms);
 
