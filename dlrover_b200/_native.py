@@ -63,6 +63,16 @@ _SIGNATURES = {
         ctypes.c_int,
         [_vp, _u32, ctypes.POINTER(_vp), ctypes.POINTER(_u64), ctypes.POINTER(_u64), _vp],
     ),
+    "fc_plan_create_mapped": (
+        ctypes.c_int,
+        [_vp, _u32, ctypes.POINTER(_vp), ctypes.POINTER(_u64), ctypes.POINTER(_u64),
+         ctypes.POINTER(_u64), _u32, ctypes.POINTER(_vp)],
+    ),
+    "fc_plan_update_mapped": (
+        ctypes.c_int,
+        [_vp, _u32, ctypes.POINTER(_vp), ctypes.POINTER(_u64), ctypes.POINTER(_u64),
+         ctypes.POINTER(_u64), _vp],
+    ),
     "fc_plan_destroy": (ctypes.c_int, [_vp]),
     "fc_plan_info": (
         ctypes.c_int,
@@ -171,6 +181,13 @@ def _stream_ptr(stream) -> Optional[int]:
     return int(stream.cuda_stream) or None
 
 
+def _plan_key(ptrs, offsets, nbytes, host_offsets=None):
+    key = ([int(p) for p in ptrs], [int(o) for o in offsets], [int(b) for b in nbytes])
+    if host_offsets is not None:
+        key += ([int(o) for o in host_offsets],)
+    return key
+
+
 class Plan:
     """Cached descriptor table of one state_dict structure (fc_plan)."""
 
@@ -203,15 +220,21 @@ class Plan:
         return self._h
 
     def update(self, ptrs: Sequence[int], offsets: Sequence[int], nbytes: Sequence[int],
-               stream=None):
+               stream=None, host_offsets: Optional[Sequence[int]] = None):
         """Re-target the plan (stream-ordered table upload, no device sync)."""
         n = len(ptrs)
         a_ptr = (_vp * max(n, 1))(*[int(p) for p in ptrs])
         a_off = (_u64 * max(n, 1))(*[int(o) for o in offsets])
         a_len = (_u64 * max(n, 1))(*[int(b) for b in nbytes])
-        _check(load_library().fc_plan_update(self.handle, n, a_ptr, a_off, a_len,
-                                             _stream_ptr(stream)), "fc_plan_update")
-        self.key = ([int(p) for p in ptrs], [int(o) for o in offsets], [int(b) for b in nbytes])
+        if host_offsets is None:
+            _check(load_library().fc_plan_update(self.handle, n, a_ptr, a_off, a_len,
+                                                 _stream_ptr(stream)), "fc_plan_update")
+        else:
+            a_host = (_u64 * max(n, 1))(*[int(o) for o in host_offsets])
+            _check(load_library().fc_plan_update_mapped(self.handle, n, a_ptr, a_off, a_host,
+                                                        a_len, _stream_ptr(stream)),
+                   "fc_plan_update_mapped")
+        self.key = _plan_key(ptrs, offsets, nbytes, host_offsets)
         self._refresh_info()
 
     def pack(self, stream=None, variant: int = VARIANT_AUTO):
@@ -348,21 +371,31 @@ class Context:
 
     # -- plans ----------------------------------------------------------------
     def plan(self, ptrs: Sequence[int], offsets: Sequence[int], nbytes: Sequence[int],
-             chunk_bytes: int = 0) -> Plan:
+             chunk_bytes: int = 0, host_offsets: Optional[Sequence[int]] = None) -> Plan:
+        """offsets: arena offsets; host_offsets (default: the same — the arena is an image
+        of the segment): where each range goes in the host segment."""
         n = len(ptrs)
-        if not (n == len(offsets) == len(nbytes)):
+        if not (n == len(offsets) == len(nbytes)) or \
+                (host_offsets is not None and len(host_offsets) != n):
             raise NativeError(FC_EINVAL, "plan", "ptrs/offsets/nbytes differ in length")
         a_ptr = (_vp * max(n, 1))(*[int(p) for p in ptrs])
         a_off = (_u64 * max(n, 1))(*[int(o) for o in offsets])
         a_len = (_u64 * max(n, 1))(*[int(b) for b in nbytes])
         h = _vp()
-        _check(
-            load_library().fc_plan_create(self.handle, n, a_ptr, a_off, a_len, int(chunk_bytes),
-                                          ctypes.byref(h)),
-            "fc_plan_create",
-        )
-        key = ([int(p) for p in ptrs], [int(o) for o in offsets], [int(b) for b in nbytes])
-        return Plan(self, h.value, key)
+        if host_offsets is None:
+            _check(
+                load_library().fc_plan_create(self.handle, n, a_ptr, a_off, a_len,
+                                              int(chunk_bytes), ctypes.byref(h)),
+                "fc_plan_create",
+            )
+        else:
+            a_host = (_u64 * max(n, 1))(*[int(o) for o in host_offsets])
+            _check(
+                load_library().fc_plan_create_mapped(self.handle, n, a_ptr, a_off, a_host, a_len,
+                                                     int(chunk_bytes), ctypes.byref(h)),
+                "fc_plan_create_mapped",
+            )
+        return Plan(self, h.value, _plan_key(ptrs, offsets, nbytes, host_offsets))
 
     def launch_count(self) -> Tuple[int, int]:
         k, m = _u64(), _u64()

@@ -17,14 +17,15 @@ struct __align__(16) FcItem {
 };
 static_assert(sizeof(FcItem) == 32, "FcItem must be 32 bytes");
 
-struct FcRun {  // merged contiguous arena range (drain/fill DMA granularity)
-  uint64_t off;
+struct FcRun {  // merged range, contiguous in the arena AND in the segment (DMA granularity)
+  uint64_t off;   // arena offset
   uint64_t len;
+  uint64_t hoff;  // offset in the host segment (== off unless the plan compacts the arena)
 };
 
-struct FcSpan {  // one input range (a tensor's bytes), ascending arena offset
+struct FcSpan {  // one input range (a tensor's bytes), ascending SEGMENT offset
   uint64_t tptr;
-  uint64_t off;
+  uint64_t off;   // offset in the host segment
   uint64_t len;
 };
 

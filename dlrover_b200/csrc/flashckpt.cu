@@ -335,7 +335,7 @@ static void pump_main(fc_ctx* c) {
         c->cv.notify_all();
       }
       for (const FcRun& r : job.runs)
-        stage_pieces(pieces, c->arena + (r.off - job.arena_base), job.host + r.off, r.len,
+        stage_pieces(pieces, c->arena + (r.off - job.arena_base), job.host + r.hoff, r.len,
                      c->stage_slot);
       if (e == cudaSuccess) e = stage_run(c, pieces, true, c->ev_pack_end, job.staged_threads);
       copies += pieces.size();
@@ -343,7 +343,7 @@ static void pump_main(fc_ctx* c) {
       job.direct = false;
     }
     // a range registered slice by slice: no DMA may straddle two slices
-    const uint64_t first_off = !job.runs.empty() ? job.runs.front().off
+    const uint64_t first_off = !job.runs.empty() ? job.runs.front().hoff
                                : !job.spans.empty() ? job.spans.front().off : 0;
     const SliceClip clip(c, job.host + first_off);
     if (job.direct) {
@@ -381,7 +381,7 @@ static void pump_main(fc_ctx* c) {
     cudaStream_t last_stream = c->copy_stream;
     for (const FcRun& r : job.runs) {
       for (uint64_t o = 0, len = 0; o < r.len && e == cudaSuccess; o += len) {
-        uint8_t* dst = job.host + r.off + o;
+        uint8_t* dst = job.host + r.hoff + o;
         len = clip(dst, std::min<uint64_t>(c->drain_piece, r.len - o));
         const uint8_t* src = c->arena + (r.off - job.arena_base) + o;
         if (pingpong) {
@@ -442,6 +442,12 @@ struct fc_plan {
   FcTable resid;  // heads and tails of congruent ranges (TMA variant)
   FcTable shift;  // ranges not congruent mod 16 (TMA variant: fc_copy_tma_shift)
   uint64_t payload = 0, arena_end = 0;
+  // extent of the plan in the host segment; identity: segment offset == arena offset for
+  // every range (the arena is a byte image of the segment).  A compacting plan
+  // (fc_plan_create_mapped) packs ranges that are scattered over the segment into a
+  // small arena; hybrid / bounded-arena saves need the identity.
+  uint64_t host_lo = 0, host_hi = 0;
+  bool identity = true;
   uint32_t chunk = kDefaultChunk;
   std::vector<FcRun> runs;
   std::vector<FcItem> h_all;  // host copy of `all`, ascending arena offset
@@ -983,10 +989,11 @@ static int table_set(fc_ctx* c, FcTable& t, const std::vector<FcItem>& v, cudaSt
 // (Re)build the plan's runs and work tables from n ranges.
 static int plan_fill(fc_plan* p, uint32_t n, const void* const* dev_ptrs,
                      const uint64_t* arena_off, const uint64_t* nbytes, cudaStream_t s,
-                     bool sync) {
+                     bool sync, const uint64_t* host_off = nullptr) {
   fc_ctx* c = p->ctx;
   const uint32_t chunk_bytes = p->chunk;
-  uint64_t payload = 0, arena_end = 0;
+  uint64_t payload = 0, arena_end = 0, host_lo = ~0ull, host_hi = 0;
+  bool identity = true;
   std::vector<FcRun> ranges, runs;
   std::vector<FcSpan> spans;
   ranges.reserve(n);
@@ -996,11 +1003,17 @@ static int plan_fill(fc_plan* p, uint32_t n, const void* const* dev_ptrs,
     if (!dev_ptrs[i])
       return fail(FC_EINVAL, "plan: null device pointer for a non-empty tensor%s%s");
     if (arena_off[i] + nbytes[i] < arena_off[i]) return fail(FC_EINVAL, "plan: offset overflow%s%s");
-    ranges.push_back({arena_off[i], nbytes[i]});
-    spans.push_back({(uint64_t)(uintptr_t)dev_ptrs[i], arena_off[i], nbytes[i]});
+    const uint64_t hoff = host_off ? host_off[i] : arena_off[i];
+    if (hoff + nbytes[i] < hoff) return fail(FC_EINVAL, "plan: offset overflow%s%s");
+    ranges.push_back({arena_off[i], nbytes[i], hoff});
+    spans.push_back({(uint64_t)(uintptr_t)dev_ptrs[i], hoff, nbytes[i]});
     payload += nbytes[i];
     arena_end = std::max(arena_end, arena_off[i] + nbytes[i]);
+    host_lo = std::min(host_lo, hoff);
+    host_hi = std::max(host_hi, hoff + nbytes[i]);
+    if (hoff != arena_off[i]) identity = false;
   }
+  if (ranges.empty()) host_lo = 0;
   std::sort(ranges.begin(), ranges.end(),
             [](const FcRun& a, const FcRun& b) { return a.off < b.off; });
   for (const FcRun& r : ranges) {
@@ -1008,7 +1021,7 @@ static int plan_fill(fc_plan* p, uint32_t n, const void* const* dev_ptrs,
       FcRun& last = runs.back();
       if (r.off < last.off + last.len)
         return fail(FC_EINVAL, "plan: tensors overlap in the arena%s%s");
-      if (r.off == last.off + last.len) {
+      if (r.off == last.off + last.len && r.hoff == last.hoff + last.len) {
         last.len += r.len;
         continue;
       }
@@ -1071,6 +1084,18 @@ static int plan_fill(fc_plan* p, uint32_t n, const void* const* dev_ptrs,
   if (rc) return rc;
   p->payload = payload;
   p->arena_end = arena_end;
+  p->host_lo = host_lo;
+  p->host_hi = host_hi;
+  p->identity = identity;
+  if (!identity) {
+    // host ranges must not overlap either
+    std::vector<FcSpan> by_host(spans);
+    std::sort(by_host.begin(), by_host.end(),
+              [](const FcSpan& a, const FcSpan& b) { return a.off < b.off; });
+    for (size_t i = 1; i < by_host.size(); ++i)
+      if (by_host[i].off < by_host[i - 1].off + by_host[i - 1].len)
+        return fail(FC_EINVAL, "plan: tensors overlap in the segment%s%s");
+  }
   p->runs.swap(runs);
   p->h_all.swap(all);
   p->pos_bulk.swap(pos_bulk);
@@ -1129,6 +1154,42 @@ extern "C" int fc_plan_update(fc_plan* p, uint32_t n, const void* const* dev_ptr
   // a kernel of this plan queued on ANOTHER stream must not see the new table
   FC_CUDA(cudaStreamWaitEvent(s, p->ev_last_use, 0));
   rc = plan_fill(p, n, dev_ptrs, arena_off, nbytes, s, /*sync=*/false);
+  if (rc) return rc;
+  FC_CUDA(cudaEventRecord(p->ev_upload, s));
+  return FC_OK;
+}
+
+extern "C" int fc_plan_create_mapped(fc_ctx* c, uint32_t n, const void* const* dev_ptrs,
+                                     const uint64_t* arena_off, const uint64_t* host_off,
+                                     const uint64_t* nbytes, uint32_t chunk_bytes,
+                                     fc_plan** out) {
+  if (!host_off && n) return fail(FC_EINVAL, "fc_plan_create_mapped: null host_off%s%s");
+  int rc = fc_plan_create(c, 0, nullptr, nullptr, nullptr, chunk_bytes, out);
+  if (rc) return rc;
+  FC_GUARD(c);
+  rc = plan_fill(*out, n, dev_ptrs, arena_off, nbytes, nullptr, /*sync=*/true, host_off);
+  if (rc) {
+    fc_plan_destroy(*out);
+    *out = nullptr;
+  }
+  return rc;
+}
+
+extern "C" int fc_plan_update_mapped(fc_plan* p, uint32_t n, const void* const* dev_ptrs,
+                                     const uint64_t* arena_off, const uint64_t* host_off,
+                                     const uint64_t* nbytes, void* stream) {
+  if (!p || (n && (!dev_ptrs || !arena_off || !host_off || !nbytes)))
+    return fail(FC_EINVAL, "fc_plan_update_mapped: null argument%s%s");
+  fc_ctx* c = p->ctx;
+  FC_GUARD(c);
+  int rc = refresh_inflight(c);
+  if (rc) return rc;
+  if (c->save_inflight || c->restore_inflight)
+    return fail(FC_EBUSY, "fc_plan_update_mapped: a save/restore is still in flight%s%s");
+  FC_CUDA(cudaEventSynchronize(p->ev_upload));
+  cudaStream_t s = (cudaStream_t)stream;
+  FC_CUDA(cudaStreamWaitEvent(s, p->ev_last_use, 0));
+  rc = plan_fill(p, n, dev_ptrs, arena_off, nbytes, s, /*sync=*/false, host_off);
   if (rc) return rc;
   FC_CUDA(cudaEventRecord(p->ev_upload, s));
   return FC_OK;
@@ -1454,7 +1515,7 @@ static int save_async_impl(fc_plan* p, void* host_base, void* compute_stream, ui
     return fail(FC_EBUSY, "fc_save_async: previous save/restore still draining%s%s");
   cudaStream_t cs = (cudaStream_t)compute_stream;
   if (p->arena_end > c->arena_bytes) {
-    if (c->arena_bytes < (8ull << 20))
+    if (c->arena_bytes < (8ull << 20) || !p->identity)
       return fail(FC_EINVAL, "arena smaller than the plan: call fc_arena_reserve first%s%s");
     rc = save_windowed(p, static_cast<uint8_t*>(host_base), cs);
     if (rc) return rc;
@@ -1475,8 +1536,8 @@ static int save_async_impl(fc_plan* p, void* host_base, void* compute_stream, ui
   FC_CUDA(cudaEventRecord(c->ev_pack_end, cs));
   const int staged =
       p->runs.empty() ? 0
-                      : staged_threads_for(c, static_cast<uint8_t*>(host_base) + p->runs.front().off,
-                                           p->arena_end - p->runs.front().off);
+                      : staged_threads_for(c, static_cast<uint8_t*>(host_base) + p->host_lo,
+                                           p->host_hi - p->host_lo);
   // hand the drain to the pump thread (paced submission, see kDrainPiece)
   {
     std::lock_guard<std::mutex> lk(c->mu);
@@ -1511,6 +1572,9 @@ static int save_hybrid_impl(fc_plan* p, void* host_base, void* compute_stream, u
   if (rc) return rc;
   if (c->save_inflight || c->restore_inflight)
     return fail(FC_EBUSY, "fc_save_hybrid_async: previous save/restore still draining%s%s");
+  if (!p->identity && cut != ~0ull)
+    return fail(FC_EINVAL, "fc_save_hybrid_async: needs a plan whose arena is an image of "
+                           "the segment%s%s");
   cudaStream_t cs = (cudaStream_t)compute_stream;
   const std::vector<FcItem>& it = p->h_all;
   uint32_t n = (uint32_t)it.size();
@@ -1538,9 +1602,9 @@ static int save_hybrid_impl(fc_plan* p, void* host_base, void* compute_stream, u
   }
   FC_CUDA(cudaEventRecord(c->ev_pack_end, cs));
   const int staged =
-      p->runs.empty() ? 0
-                      : staged_threads_for(c, static_cast<uint8_t*>(host_base) + p->runs.front().off,
-                                           p->arena_end - p->runs.front().off);
+      p->spans.empty() ? 0
+                       : staged_threads_for(c, static_cast<uint8_t*>(host_base) + p->host_lo,
+                                            p->host_hi - p->host_lo);
   {
     std::lock_guard<std::mutex> lk(c->mu);
     if (c->drain_rc != FC_OK) return fail(c->drain_rc, "%s", c->drain_err.c_str());
@@ -1553,7 +1617,7 @@ static int save_hybrid_impl(fc_plan* p, void* host_base, void* compute_stream, u
       if (sp.off < cut) job.spans.push_back(sp);
     for (const FcRun& r : p->runs) {
       uint64_t a = std::max(r.off, cut), b = r.off + r.len;
-      if (b > a) job.runs.push_back({a, b - a});
+      if (b > a) job.runs.push_back({a, b - a, a});
     }
     job.direct = true;
     job.arena_base = abase;
@@ -1594,9 +1658,7 @@ extern "C" int fc_restore_direct_async(fc_plan* p, const void* host_base, void* 
   FC_CUDA(cudaStreamWaitEvent(c->copy_stream, c->ev_scatter_end, 0));
   FC_CUDA(cudaEventRecord(c->ev_fill_start, c->copy_stream));
   const int staged =
-      p->spans.empty() ? 0
-                       : staged_threads_for(c, hb + p->spans.front().off,
-                                            p->arena_end - p->spans.front().off);
+      p->spans.empty() ? 0 : staged_threads_for(c, hb + p->host_lo, p->host_hi - p->host_lo);
   if (staged > 0) {
     // unregistered segment (a restarted trainer): bounce slots, blocks until the data
     // is on the device
@@ -1612,7 +1674,7 @@ extern "C" int fc_restore_direct_async(fc_plan* p, const void* host_base, void* 
     c->restore_inflight = true;
     return FC_OK;
   }
-  const SliceClip clip(c, p->spans.empty() ? hb : hb + p->spans.front().off);
+  const SliceClip clip(c, hb + p->host_lo);
   for (const FcSpan& sp : p->spans)
     for (uint64_t o = 0, len = 0; o < sp.len; o += len) {
       len = clip(hb + sp.off + o, std::min<uint64_t>(kDmaPiece, sp.len - o));
@@ -1859,7 +1921,7 @@ extern "C" int fc_restore_async(fc_plan* p, const void* host_base, void* stream)
   if (c->save_inflight || c->restore_inflight)
     return fail(FC_EBUSY, "fc_restore_async: arena busy%s%s");
   if (p->arena_end > c->arena_bytes) {
-    if (c->arena_bytes < (8ull << 20))
+    if (c->arena_bytes < (8ull << 20) || !p->identity)
       return fail(FC_EINVAL, "arena smaller than the plan: call fc_arena_reserve first%s%s");
     rc = restore_windowed(p, static_cast<const uint8_t*>(host_base), (cudaStream_t)stream);
     if (rc) return rc;
@@ -1870,13 +1932,11 @@ extern "C" int fc_restore_async(fc_plan* p, const void* host_base, void* stream)
   const uint8_t* hb = static_cast<const uint8_t*>(host_base);
   FC_CUDA(cudaEventRecord(c->ev_fill_start, c->copy_stream));
   const int staged =
-      p->runs.empty() ? 0
-                      : staged_threads_for(c, hb + p->runs.front().off,
-                                           p->arena_end - p->runs.front().off);
+      p->runs.empty() ? 0 : staged_threads_for(c, hb + p->host_lo, p->host_hi - p->host_lo);
   if (staged > 0) {
     std::vector<StagePiece> pieces;
     for (const FcRun& r : p->runs)
-      stage_pieces(pieces, c->arena + r.off, const_cast<uint8_t*>(hb) + r.off, r.len,
+      stage_pieces(pieces, c->arena + r.off, const_cast<uint8_t*>(hb) + r.hoff, r.len,
                    c->stage_slot);
     cudaError_t e = stage_run(c, pieces, false, nullptr, staged);
     if (e != cudaSuccess) return fail(FC_ECUDA, "staged restore: %s", cudaGetErrorString(e));
@@ -1888,11 +1948,11 @@ extern "C" int fc_restore_async(fc_plan* p, const void* host_base, void* stream)
     c->restore_inflight = true;
     return FC_OK;
   }
-  const SliceClip clip(c, p->runs.empty() ? hb : hb + p->runs.front().off);
+  const SliceClip clip(c, hb + p->host_lo);
   for (const FcRun& r : p->runs)
     for (uint64_t o = 0, len = 0; o < r.len; o += len) {
-      len = clip(hb + r.off + o, std::min<uint64_t>(kDmaPiece, r.len - o));
-      FC_CUDA(cudaMemcpyAsync(c->arena + r.off + o, hb + r.off + o, len, cudaMemcpyHostToDevice,
+      len = clip(hb + r.hoff + o, std::min<uint64_t>(kDmaPiece, r.len - o));
+      FC_CUDA(cudaMemcpyAsync(c->arena + r.off + o, hb + r.hoff + o, len, cudaMemcpyHostToDevice,
                               c->copy_stream));
       c->n_memcpys += 1;
     }

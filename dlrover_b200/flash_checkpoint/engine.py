@@ -439,7 +439,41 @@ class CheckpointEngine(metaclass=ABCMeta):
                 return False
         return True
 
-    def _cooperative_save(self, state_dict, conf: CheckpointConfig, blocking: bool) -> bool:
+    def full_from_shards_supported(self) -> bool:
+        """True when this engine can assemble a FULL checkpoint from a state dict of shards
+        without gathering them (save_shards_to_memory): cooperative saves are on and every
+        rank of the job is local to this node (each shard must reach THIS node's segment)."""
+        return self._cooperative() and self._world_size == env_utils.get_local_world_size()
+
+    def save_shards_to_memory(self, step, sharded_state_dict, paths: Dict[str, str],
+                              blocking=False) -> bool:
+        """`sharded_state_dict`: {state name: tree whose tensor leaves are this rank's
+        SHARDS (DTensor / ShardedTensor) or replicated tensors}.  The segment receives the
+        FULL image — what save_to_memory would write for the gathered state dict
+        (reference fsdp.py:238-262: FULL_STATE_DICT all-gather, then one rank saves) — each
+        rank contributing its shards over its own PCIe link."""
+        if not self.full_from_shards_supported():
+            raise RuntimeError("save_shards_to_memory needs cooperative saves on a single node")
+        conf = CheckpointConfig(step=step, paths=paths)
+        return self._cooperative_save(sharded_state_dict, conf, blocking, shards=True)
+
+    def save_shards_to_storage(self, step, sharded_state_dict, paths: Dict[str, str],
+                               blocking=False) -> bool:
+        """save_shards_to_memory + tell the agent to persist the step (the file the agent
+        writes is the FULL checkpoint, as after save_to_storage of the gathered state)."""
+        success = True
+        if step > self._cached_step:
+            success = self.save_shards_to_memory(step, sharded_state_dict, paths, blocking)
+        if dist.is_initialized():
+            dist.barrier()
+        if success and self._local_rank == 0:
+            self._notify_save_event(step)
+        if success:
+            self.latest_step = step
+        return success
+
+    def _cooperative_save(self, state_dict, conf: CheckpointConfig, blocking: bool,
+                          shards: bool = False) -> bool:
         handler = self._shm_handler
         local_world = env_utils.get_local_world_size()
         leader = self._local_rank == 0
@@ -477,9 +511,15 @@ class CheckpointEngine(metaclass=ABCMeta):
                 self._shm_lock.release()
 
         try:
-            handler.save_state_dict(state_dict, blocking=not self._async_drain or blocking,
-                                    on_complete=completed, on_error=failed,
-                                    stream=self.snapshot_stream, coop=coop)
+            if shards:
+                handler.save_shards_as_full(state_dict, coop,
+                                            blocking=not self._async_drain or blocking,
+                                            stream=self.snapshot_stream, on_complete=completed,
+                                            on_error=failed)
+            else:
+                handler.save_state_dict(state_dict, blocking=not self._async_drain or blocking,
+                                        on_complete=completed, on_error=failed,
+                                        stream=self.snapshot_stream, coop=coop)
         except BaseException:
             if acquired and handler.pending_save() is None and self._shm_lock.locked():
                 self._shm_lock.release()

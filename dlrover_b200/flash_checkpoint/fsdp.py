@@ -124,11 +124,37 @@ class FsdpFullCheckpointer(Checkpointer):
                                     FullStateDictConfig(rank0_only=False),
                                     FullOptimStateDictConfig(rank0_only=False))
 
+    def _from_shards(self) -> bool:
+        """The FULL checkpoint can be assembled from every rank's SHARDED state dict
+        (no FULL_STATE_DICT all-gather, no full replica in every rank's HBM) when the
+        ranks of the job all sit on this node and save cooperatively."""
+        return os.getenv("DLROVER_B200_FULL_FROM_SHARDS", "1") not in ("0", "false", "False") \
+            and self._engine.full_from_shards_supported()
+
     def save_checkpoint(self, step, model, optimizer, extra_sd={}, path="",
                         storage_type=StorageType.DISK):
         if path == "":
+            # one image per node, written under the node's saving rank (local rank 0)
             path = os.path.join(self.checkpoint_dir, f"{step}/rank_{self._rank}.pt")
         self._engine.guard_if_in_place(optimizer)
+        if self._from_shards():
+            path = os.path.join(os.path.dirname(path), "rank_0.pt") if path.endswith(
+                f"rank_{self._rank}.pt") else path
+            with FSDP.state_dict_type(model, StateDictType.SHARDED_STATE_DICT):
+                state_dict = {"model": model.state_dict(),
+                              "optimizer": FSDP.optim_state_dict(model, optimizer)}
+            state_dict.update(extra_sd)
+            if storage_type == StorageType.MEMORY:
+                return self._engine.save_shards_to_memory(step, {_MODEL: state_dict},
+                                                          {_MODEL: path})
+            if storage_type == StorageType.DISK:
+                if not path:
+                    raise ValueError("path cannot be empty if storage type is disk!")
+                if self._rank == 0:
+                    self.storage.safe_rmtree(os.path.dirname(path))
+                return self._engine.save_shards_to_storage(step, {_MODEL: state_dict},
+                                                           {_MODEL: path})
+            raise ValueError(f"No support storage type {storage_type}")
         with self._full_state(model):
             state_dict = {"model": model.state_dict(),
                           "optimizer": FSDP.optim_state_dict(model, optimizer)}

@@ -220,6 +220,126 @@ def plan_layout(state_dict, prev: Optional["_Layout"] = None) -> _Layout:
     return lay
 
 
+def _local_boxes(value):
+    """A sharded leaf as (full shape, dtype, [(local tensor, offsets in the full tensor)])
+    or None for anything else.  Understands DTensor (FSDP2, any mesh / placements torch can
+    turn into a global offset) and ShardedTensor (FSDP1 SHARDED_STATE_DICT)."""
+    if not torch.is_tensor(value) and not hasattr(value, "local_shards"):
+        return None
+    placements = getattr(value, "placements", None)
+    if placements is not None and hasattr(value, "to_local"):
+        from torch.distributed.tensor._utils import compute_local_shape_and_global_offset
+
+        local = value.to_local()
+        _, offsets = compute_local_shape_and_global_offset(value.shape, value.device_mesh,
+                                                           placements)
+        return tuple(value.shape), value.dtype, [(local, tuple(int(o) for o in offsets))]
+    shards = getattr(value, "local_shards", None)
+    if callable(shards):
+        return (tuple(value.size()), value.dtype,
+                [(sh.tensor, tuple(int(o) for o in sh.metadata.shard_offsets)) for sh in shards()])
+    return None
+
+
+def _box_ranges(local: torch.Tensor, offsets, full_shape, full_off: int):
+    """(tensor piece, segment offset, nbytes) for a local box of a row-major full tensor
+    that starts at `full_off` in the segment.  A dim-0 shard (every other dim complete) is
+    one contiguous range; anything else is one range per run of complete trailing dims."""
+    es = local.element_size()
+    shape = tuple(local.shape)
+    if local.numel() == 0:
+        return []
+    if len(shape) != len(full_shape):
+        raise ValueError(f"local shard {shape} vs full tensor {tuple(full_shape)}")
+    # trailing dims that the box covers completely
+    k = len(shape)
+    while k > 1 and shape[k - 1] == full_shape[k - 1]:
+        k -= 1
+    # the run = dims [k-1:] of the box (dim k-1 may be partial), rows = dims [:k-1]
+    stride = [1] * len(full_shape)
+    for d in range(len(full_shape) - 2, -1, -1):
+        stride[d] = stride[d + 1] * full_shape[d + 1]
+    run_elems = 1
+    for d in range(max(k - 1, 0), len(shape)):
+        run_elems *= shape[d]
+    lead = shape[:max(k - 1, 0)]
+    n_rows = 1
+    for d in lead:
+        n_rows *= d
+    if n_rows > (1 << 16):
+        raise ValueError("local shard decomposes into too many rows")
+    local = local.detach()
+    if not local.is_contiguous():
+        local = local.contiguous()
+    flat = local.reshape(n_rows, run_elems) if n_rows > 1 else local.reshape(1, run_elems)
+    out = []
+    idx = [0] * len(lead)
+    for r in range(n_rows):
+        elem = sum((offsets[d] + idx[d]) * stride[d] for d in range(len(lead)))
+        if k >= 1:
+            elem += offsets[k - 1] * stride[k - 1] if len(shape) else 0
+        out.append((flat[r], full_off + elem * es, run_elems * es))
+        for d in range(len(lead) - 1, -1, -1):
+            idx[d] += 1
+            if idx[d] < lead[d]:
+                break
+            idx[d] = 0
+    return out
+
+
+def plan_layout_full_from_shards(state_dict):
+    """Layout of the FULL (unsharded) state — the one `plan_layout` gives for the gathered
+    state dict (reference fsdp.py:238-262 + ckpt_saver.py:286-301) — computed from a state
+    dict whose leaves are this rank's SHARDS.  Returns (_Layout, mine) where the layout's
+    device/host leaves are the replicated tensors (every rank holds them) and `mine` the
+    (tensor piece, segment offset, nbytes) ranges only this rank can write."""
+    lay = _Layout()
+    metas = lay.leaf_metas
+    mine = []
+    total = 0
+
+    def walk(value):
+        nonlocal total
+        boxes = _local_boxes(value)
+        if boxes is not None:
+            full_shape, dtype, locals_ = boxes
+            numel = 1
+            for d in full_shape:
+                numel *= d
+            es = torch.empty(0, dtype=dtype).element_size()
+            m = TensorMeta(shape=tuple(full_shape), dtype=dtype, element_size=es, numel=numel,
+                           offset=total)
+            metas.append(m)
+            for local, offsets in locals_:
+                mine.extend(_box_ranges(local, offsets, full_shape, total))
+            total += numel * es
+            return m
+        if isinstance(value, torch.Tensor):
+            m = TensorMeta(shape=tuple(value.shape), dtype=value.dtype,
+                           element_size=value.element_size(), numel=value.numel(), offset=total)
+            metas.append(m)
+            nbytes = m.numel * m.element_size
+            if nbytes:
+                total += nbytes
+                (lay.device_leaves if value.is_cuda else lay.host_leaves).append((value, m))
+            return m
+        if isinstance(value, Mapping):
+            return {k: walk(v) for k, v in value.items()}
+        if isinstance(value, list):
+            return [walk(v) for v in value]
+        if type(value) not in _IMMUTABLE_LEAVES:
+            try:
+                value = copy.deepcopy(value)
+            except Exception:
+                pass
+        lay.extras.append(value)
+        return value
+
+    lay.meta = walk(state_dict)
+    lay.total = total
+    return lay, mine
+
+
 def _read_tensor_from_buf(value, shm: SharedMemory):
     if not isinstance(value, TensorMeta):
         return value
@@ -330,6 +450,24 @@ def _row_ranges(t: torch.Tensor, off: int, max_rows: int = 1 << 16, min_row_byte
 
 def _triples(leaves):
     return [(t, m.offset, m.numel * m.element_size) for t, m in leaves]
+
+
+def _clip_triples(triples, lo: int, hi: int):
+    """(tensor, segment offset, nbytes) triples cut to segment bytes [lo, hi): the part of
+    a tensor that falls inside becomes a uint8 view on its bytes."""
+    out = []
+    for t, off, n in triples:
+        a, b = max(off, lo), min(off + n, hi)
+        if b <= a:
+            continue
+        if a == off and b == off + n:
+            out.append((t, off, n))
+            continue
+        flat = t.detach()
+        if not flat.is_contiguous():
+            flat = flat.contiguous()
+        out.append((flat.reshape(-1).view(torch.uint8)[a - off:b - off], a, b - a))
+    return out
 
 
 def _clip_ranges(prepared, lo: int, hi: int):
@@ -450,7 +588,8 @@ class _DeviceStager:
                 lens.append(n)
         return ptrs, offs, lens
 
-    def plan_for(self, prepared, role: str = "save", stream=None, base: int = 0):
+    def plan_for(self, prepared, role: str = "save", stream=None, base: int = 0,
+                 compact: bool = False):
         """prepared: (ptrs, segment offsets, lengths) from prepare_ranges.  `base` is
         subtracted from the offsets (a window of the segment staged on its own: arena
         byte 0 = segment byte `base`, the host base moves by the same amount).
@@ -460,14 +599,23 @@ class _DeviceStager:
         ptrs, offs, lens = prepared
         if base:
             offs = [o - base for o in offs]
-        key = (ptrs, offs, lens)
+        host_offs = None
+        if compact:
+            # ranges scattered over the segment, packed into a small arena; every arena
+            # offset congruent to its source mod 16: all of them take the bulk (TMA) kernel
+            host_offs, offs, a = offs, [], 0
+            for p, n in zip(ptrs, lens):
+                a += (p - a) % 16
+                offs.append(a)
+                a += n
+        key = native._plan_key(ptrs, offs, lens, host_offs)
         plan = self._plans.get(role)
         if plan is not None and plan.key == key:
             return plan
         if plan is None:
-            plan = self._plans[role] = self.ctx.plan(ptrs, offs, lens)
+            plan = self._plans[role] = self.ctx.plan(ptrs, offs, lens, host_offsets=host_offs)
         else:
-            plan.update(ptrs, offs, lens, stream)
+            plan.update(ptrs, offs, lens, stream, host_offsets=host_offs)
         return plan
 
     ARENA_FULL, ARENA_WINDOWED, ARENA_NONE = "full", "windowed", "none"
@@ -874,7 +1022,7 @@ class SharedMemoryHandler:
                      pre_drain: Optional[Callable[[], None]] = None,
                      on_error: Optional[Callable[[], None]] = None,
                      in_place: Optional[bool] = None,
-                     window: Optional[Tuple[int, int]] = None):
+                     window: Optional[Tuple[int, int]] = None, compact: bool = False):
         """Move bytes into the (already sized) segment.
 
         device_ranges / host_ranges: (tensor, segment offset, nbytes) for CUDA /
@@ -952,8 +1100,8 @@ class SharedMemoryHandler:
                 # stream has enqueued so far, and the caller must make the training
                 # stream wait for `last_pack_event` before it MUTATES the tensors
                 stream.wait_stream(current)
-            plan = stager.plan_for(prepared, role="save", stream=stream, base=lo)
-            in_place = self.in_place if in_place is None else in_place
+            plan = stager.plan_for(prepared, role="save", stream=stream, base=lo, compact=compact)
+            in_place = (self.in_place if in_place is None else in_place) and not compact
             cut = None  # hybrid: window offset from which the tensors are snapshotted
             if in_place:
                 arena = stager.ARENA_NONE
@@ -1174,8 +1322,21 @@ class SharedMemoryHandler:
                                  pre_drain=announce if defer_announce else None,
                                  on_error=on_error)
 
+    def save_shards_as_full(self, state_dict, coop: CoopContext, blocking: bool = True,
+                            stream=None, on_complete=None, on_error=None):
+        """Cooperative save of the FULL state from a state dict of SHARDS (DTensor /
+        ShardedTensor leaves, e.g. FSDP's sharded state dict): the segment gets the image the
+        gathered state dict would have produced, but nobody gathers anything — every rank
+        drains its own shards to where they belong in the full tensors (plus its slice of
+        the replicated leaves).  All ranks that hold shards must be local to this node."""
+        self.wait_pending()
+        lay, mine = plan_layout_full_from_shards(state_dict)
+        self._layout = None  # not comparable with a plain layout
+        return self._save_cooperative(state_dict, lay, coop, blocking, stream, on_complete,
+                                      on_error, mine=mine)
+
     def _save_cooperative(self, state_dict, lay: _Layout, coop: CoopContext, blocking, stream,
-                          on_complete, on_error):
+                          on_complete, on_error, mine=None):
         meta_dict = lay.meta
         conf: CheckpointConfig = meta_dict[DLROVER_CKPT_CONFIG_KEY]
         total = lay.total
@@ -1226,11 +1387,20 @@ class SharedMemoryHandler:
                 if on_error is not None:
                     on_error()
 
-        keepalive = [state_dict] if lay.device_leaves else []
+        keepalive = [state_dict] if (lay.device_leaves or mine) else []
         if total == 0:
             finish()
             return None
         try:
+            if mine is not None:
+                # replicated leaves: my slice of each; sharded leaves: what only I hold
+                dev = _clip_triples(_triples(lay.device_leaves), *window) + \
+                    [r for r in mine if r[0].is_cuda]
+                host = _clip_triples(_triples(lay.host_leaves), *window) + \
+                    [r for r in mine if not r[0].is_cuda]
+                return self.write_ranges(dev, host, blocking=blocking, stream=stream,
+                                         finish=finish, keepalive=keepalive + [dev, host],
+                                         on_error=failed, compact=True)
             return self.write_ranges(_triples(lay.device_leaves), _triples(lay.host_leaves),
                                      blocking=blocking, stream=stream, finish=finish,
                                      keepalive=keepalive, on_error=failed, window=window)

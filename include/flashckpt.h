@@ -137,6 +137,21 @@ int fc_plan_create(fc_ctx* ctx, uint32_t n, const void* const* dev_ptrs,
  * synchronisation.  FC_EBUSY while a save/restore of the context is in flight. */
 int fc_plan_update(fc_plan* plan, uint32_t n, const void* const* dev_ptrs,
                    const uint64_t* arena_off, const uint64_t* nbytes, void* stream);
+/* The same with the arena offset of a range independent from its offset in the host
+ * segment (host_off[i]): ranges that are scattered over a large segment — one rank's
+ * shards of a FULL state dict that several ranks assemble in one segment — are packed
+ * into a small arena, and the drain copies arena_off -> host_off range by range (runs
+ * are merged where both sides continue).  Choosing arena_off[i] congruent to dev_ptrs[i]
+ * mod 16 sends every range through the bulk (TMA ring) kernel.  Ranges must not overlap
+ * in the arena nor in the segment.  Hybrid and bounded-arena saves need the identity
+ * mapping of fc_plan_create.  Replaces, for such a rank, the all-gather of the full
+ * tensors + the saving rank's copy loop (fsdp.py:238-262, ckpt_saver.py:198-231). */
+int fc_plan_create_mapped(fc_ctx* ctx, uint32_t n, const void* const* dev_ptrs,
+                          const uint64_t* arena_off, const uint64_t* host_off,
+                          const uint64_t* nbytes, uint32_t chunk_bytes, fc_plan** out);
+int fc_plan_update_mapped(fc_plan* plan, uint32_t n, const void* const* dev_ptrs,
+                          const uint64_t* arena_off, const uint64_t* host_off,
+                          const uint64_t* nbytes, void* stream);
 int fc_plan_destroy(fc_plan* plan);
 /* total payload bytes, number of work items, number of merged arena runs,
  * end offset (max arena_off+nbytes) */

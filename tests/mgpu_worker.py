@@ -381,7 +381,118 @@ def case_megatron(args, rank, world, dev, ckpt_dir):
     return out
 
 
-CASES = {"fsdp": case_fsdp, "ddp": case_ddp, "coop": case_coop, "zero3": case_zero3,
+def case_fullshards(args, rank, world, dev, ckpt_dir):
+    """G2: the FULL checkpoint of a sharded (FSDP-style) state assembled in ONE segment
+    without gathering: every rank drains its own shards to their place in the full
+    tensors.  Expected image = oracle image of the gathered state dict."""
+    from torch.distributed.device_mesh import init_device_mesh
+
+    from dlrover_b200 import shapes
+    from dlrover_b200.common.storage import PosixDiskStorage
+    from dlrover_b200.flash_checkpoint.engine import FullCheckpointEngine
+
+    mesh = init_device_mesh(dev.type, (world,))
+    shp = shapes.scale_shapes(shapes.llama3_8b_shapes(), args.scale)
+    factory = shapes.ShardedStateFactory(shp, world, rank, dev, mesh)
+    engine = FullCheckpointEngine(ckpt_dir, PosixDiskStorage())
+    assert engine.full_from_shards_supported()
+    handler = engine._shm_handler
+    out = {"payload_bytes_local": factory.local_bytes}
+    for step, variant in ((1, 0), (2, 1)):
+        sd = factory.build(variant)
+        t0 = time.perf_counter()
+        assert engine.save_shards_to_memory(step, {"model_states": sd},
+                                            {"model_states": os.path.join(ckpt_dir, f"{step}.pt")})
+        out["call_ms"] = (time.perf_counter() - t0) * 1e3
+        assert engine.wait_memory_save(600)
+        dist.barrier()
+        handler.refresh_mapping()
+
+        # what a gather would have produced
+        def gathered(t):
+            if not hasattr(t, "to_local"):
+                return t
+            local = t.to_local().contiguous()
+            parts = [torch.empty_like(local) for _ in range(world)]
+            dist.all_gather(parts, local)
+            return torch.cat(parts, dim=0)
+
+        def full_tree(v):
+            if isinstance(v, dict):
+                return {k: full_tree(x) for k, x in v.items()}
+            if isinstance(v, list):
+                return [full_tree(x) for x in v]
+            return gathered(v) if torch.is_tensor(v) else v
+
+        full = full_tree(sd)
+        out.update(compare_with_oracle(handler, {"model_states": full,
+                                                 "_DLORVER_CKPT_CONFIG": None}, args.full_compare))
+        meta = handler.metadata.get()
+        assert meta["_DLORVER_CKPT_CONFIG"].step == step
+        assert meta["_DLORVER_CKPT_CONFIG"].writing_shm is False
+        dist.barrier()
+    loaded = engine.load()
+    k = next(iter(full["model"]))
+    assert torch.equal(loaded["model"][k], full["model"][k].cpu())
+    assert loaded["optim"]["param_groups"][0]["lr"] == 3e-4
+    del loaded
+    out["segment"] = handler.shared_memory.name
+    dist.barrier()
+    engine.close()
+    return out
+
+
+def case_fsdp_full(args, rank, world, dev, ckpt_dir):
+    """FsdpFullCheckpointer on a real torch FSDP module: the full checkpoint is assembled
+    from the ranks' SHARDED state dicts; the segment must equal the oracle image of what
+    torch's own FULL_STATE_DICT gather produces, and reloading restores the logits."""
+    import torch.nn as nn
+    from torch.distributed.fsdp import FullOptimStateDictConfig, FullStateDictConfig
+    from torch.distributed.fsdp import FullyShardedDataParallel as FSDP
+    from torch.distributed.fsdp import StateDictType
+
+    from dlrover_b200.flash_checkpoint.api import StorageType
+    from dlrover_b200.flash_checkpoint.fsdp import FsdpFullCheckpointer
+
+    torch.manual_seed(11)
+    model = nn.Sequential(nn.Linear(384, 1000), nn.GELU(), nn.LayerNorm(1000),
+                          nn.Linear(1000, 777), nn.GELU(), nn.Linear(777, 33)).to(dev)
+    fsdp = FSDP(model, device_id=dev if dev.type == "cuda" else None)
+    opt = torch.optim.AdamW(fsdp.parameters(), lr=1e-3)
+    x = torch.randn(8, 384, device=dev)
+    fsdp(x).sum().backward()
+    opt.step()
+    opt.zero_grad()
+    ckpt = FsdpFullCheckpointer(ckpt_dir)
+    assert ckpt._from_shards(), "full-from-shards path is off"
+    handler = ckpt.engine._shm_handler
+    with torch.no_grad():
+        want_logits = fsdp(x).clone()
+    ckpt.save_checkpoint(5, fsdp, opt, {"epoch": 3}, storage_type=StorageType.MEMORY)
+    assert ckpt.wait_memory_save(300)
+    dist.barrier()
+    handler.refresh_mapping()
+    with FSDP.state_dict_type(fsdp, StateDictType.FULL_STATE_DICT,
+                              FullStateDictConfig(rank0_only=False),
+                              FullOptimStateDictConfig(rank0_only=False)):
+        full = {"model": fsdp.state_dict(), "optimizer": FSDP.optim_state_dict(fsdp, opt)}
+    full["epoch"] = 3
+    out = compare_with_oracle(handler, {"model_states": full, "_DLORVER_CKPT_CONFIG": None}, 1)
+    # perturb, reload through the checkpointer, same logits
+    with torch.no_grad():
+        for p in fsdp.parameters():
+            p.add_(0.5)
+    extra = ckpt.load_checkpoint(fsdp, opt)
+    assert extra.get("epoch") == 3
+    with torch.no_grad():
+        got = fsdp(x)
+    assert torch.equal(got, want_logits), "logits differ after reload"
+    dist.barrier()
+    ckpt.engine.close()
+    return out
+
+
+CASES = {"fsdp_full": case_fsdp_full, "fullshards": case_fullshards, "fsdp": case_fsdp, "ddp": case_ddp, "coop": case_coop, "zero3": case_zero3,
          "megatron": case_megatron}
 
 

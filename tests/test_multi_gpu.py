@@ -23,7 +23,7 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 WORKER = os.path.join(ROOT, "tests", "mgpu_worker.py")
-CASES = ["fsdp", "ddp", "coop", "zero3", "megatron"]
+CASES = ["fsdp", "ddp", "coop", "fullshards", "zero3", "megatron"]
 
 
 def run_case(case, world, backend, device, extra=(), timeout=900):
@@ -68,7 +68,7 @@ def _gpus():
 @pytest.mark.gpu
 @pytest.mark.timeout(1500)
 @pytest.mark.parametrize("world", [2, 8])
-@pytest.mark.parametrize("case", CASES)
+@pytest.mark.parametrize("case", CASES + ["fsdp_full"])
 def test_nccl_ranks_on_gpus(case, world):
     if _gpus() < world:
         pytest.skip(f"needs {world} GPUs on one box, this one has {_gpus()} "
