@@ -75,17 +75,21 @@ def shard_shapes(shapes, world: int, rank: int):
 
 
 def fill_(t: torch.Tensor, seed: int) -> torch.Tensor:
-    """Cheap, seeded, non-trivial bit pattern (device-side, no big randn)."""
+    """Cheap, seeded, non-trivial bit pattern (device-side, no big randn); large tensors
+    are filled piece by piece so the temporaries stay small."""
     n = t.numel()
     if n == 0:
         return t
     flat = t.view(-1)
-    if t.dtype in (torch.float32, torch.bfloat16, torch.float16, torch.float64):
-        idx = torch.arange(n, device=t.device, dtype=torch.float32)
-        flat.copy_((torch.sin(idx * 0.001 + seed) * 0.02).to(t.dtype))
-    else:
-        idx = torch.arange(n, device=t.device, dtype=torch.int64)
-        flat.copy_(((idx * 2654435761 + seed) % 251).to(t.dtype))
+    piece = 32 << 20
+    for lo in range(0, n, piece):
+        hi = min(n, lo + piece)
+        if t.dtype in (torch.float32, torch.bfloat16, torch.float16, torch.float64):
+            idx = torch.arange(lo, hi, device=t.device, dtype=torch.float32)
+            flat[lo:hi].copy_((torch.sin(idx * 0.001 + seed) * 0.02).to(t.dtype))
+        else:
+            idx = torch.arange(lo, hi, device=t.device, dtype=torch.int64)
+            flat[lo:hi].copy_(((idx * 2654435761 + seed) % 251).to(t.dtype))
     return t
 
 

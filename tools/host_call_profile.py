@@ -24,6 +24,16 @@ sd = shapes.build_state_dict(shapes.llama3_8b_shapes(), torch.bfloat16, dev)
 for s in range(1, 4):
     ckpt.save_checkpoint(s, sd, storage_type=StorageType.MEMORY)
     ckpt.wait_memory_save()
+plain = []
+for s in range(1000, 1000 + N):
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    ckpt.save_checkpoint(s, sd, storage_type=StorageType.MEMORY)
+    plain.append(time.perf_counter() - t0)
+    ckpt.wait_memory_save()
+plain.sort()
+print(f"saves={N} host call median {plain[N // 2] * 1e3:.3f} ms  min {plain[0] * 1e3:.3f} ms  "
+      f"p90 {plain[int(N * 0.9)] * 1e3:.3f} ms (no profiler)")
 prof = cProfile.Profile()
 wall = []
 for s in range(4, 4 + N):
