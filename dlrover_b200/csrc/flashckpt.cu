@@ -503,12 +503,18 @@ extern "C" int fc_ctx_create(int device, fc_ctx** out) {
                         &c->ev_fill_start, &c->ev_fill_end,  &c->ev_scatter_end};
   for (cudaEvent_t* ev : evs)
     if (e == cudaSuccess) e = cudaEventCreate(ev);
-  // The pump spin-waits between pieces: wake-up latency matters with one piece
-  // in flight (measured: 55.6 GB/s spinning vs 52.4 GB/s with a blocking wait
-  // at 32 MiB pieces), and it costs one busy host core only while a checkpoint
-  // drains (~0.3 s).  FC_DRAIN_SPIN=0 selects the blocking wait.
+  // The host-paced pump waits for piece k before it submits piece k+1, so its wake-up
+  // latency is on the critical path: a spinning wait gives 55.6 GB/s, a blocking one
+  // 52.4 GB/s at 32 MiB pieces (profiles/r01_d2h_pacing.md).  Spinning costs one busy
+  // host core while a checkpoint drains (~0.3 s) — nothing on a 128-core GPU host, a lot
+  // in an 8-vCPU container.  Default: spin when the machine has more than 16 hardware
+  // threads; otherwise sleep in a blocking wait AND chain the pieces on the device
+  // (ping-pong mode: no host round trip between pieces, profiles/r02_drain_modes.md).
+  // FC_DRAIN_SPIN=0/1 and FC_DRAIN_MODE=0/1 override.
   const char* spin_env = getenv("FC_DRAIN_SPIN");
-  const bool drain_spin = !(spin_env && spin_env[0] == '0');
+  const bool many_cores = std::thread::hardware_concurrency() > 16;
+  const bool drain_spin = spin_env ? spin_env[0] != '0' : many_cores;
+  if (!drain_spin) c->drain_mode = FC_DRAIN_PINGPONG;
   for (int i = 0; i < kDrainRing; ++i)
     if (e == cudaSuccess)
       e = cudaEventCreateWithFlags(

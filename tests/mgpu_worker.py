@@ -38,6 +38,9 @@ def parse():
     ap.add_argument("--device", default="cuda")
     ap.add_argument("--scale", type=float, default=1 / 64, help="fraction of Llama-3-8B rows")
     ap.add_argument("--flat-mib", type=float, default=64.0, help="zero3: MiB per flat partition")
+    ap.add_argument("--layers", type=int, default=2, help="megatron: layers per pipeline stage")
+    ap.add_argument("--widths", type=float, default=0.0,
+                    help="megatron: fraction of the Mixtral widths (default: 8 x --scale)")
     ap.add_argument("--in-place", action="store_true")
     ap.add_argument("--snapshot-mib", type=int, default=0)
     ap.add_argument("--full-compare", type=int, default=1,
@@ -333,8 +336,8 @@ def case_megatron(args, rank, world, dev, ckpt_dir):
     from dlrover_b200.flash_checkpoint.engine import MegatronDistCheckpointEngine
 
     tp, pp = install_fake_megatron(rank, world)
-    scale = args.scale * 8  # --scale 1/64 -> 1/8 of the Mixtral layer widths
-    h, ffn, experts, layers = int(4096 * scale), int(14336 * scale), 8, 2
+    scale = args.widths or args.scale * 8  # --scale 1/64 -> 1/8 of the Mixtral layer widths
+    h, ffn, experts, layers = int(4096 * scale), int(14336 * scale), 8, args.layers
     model = {"args": {"tp": tp, "pp": pp}, "iteration": 20, "checkpoint_version": 3.0, "model": {}}
     for l in range(layers):
         p = f"decoder.layers.{l}."

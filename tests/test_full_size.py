@@ -2,7 +2,15 @@
 through size-independent properties — a checksum of per-tensor checksums of the
 segment equals the same checksum computed on the device, spot byte-compares,
 and save -> zero -> restore -> torch.equal on every tensor; plus the AdamW-style
-misaligned layout at 1/8 size."""
+misaligned layout at 1/8 size.
+
+What this is and is not: the 16 GB image is NOT compared byte for byte with an oracle
+image (numpy would need the 16 GB twice and minutes).  Checked at full size: every
+tensor's offset against the oracle's layout plan, the checksum of per-tensor checksums
+(device side vs segment), 64 KiB at the head and tail of every 37th tensor byte for
+byte, and the bit-exact round trip.  The byte-for-byte comparison against the oracle
+image is done at 1/8 size (AdamW layout, below) and on the fixtures of
+tests/test_gpu_kernels.py / tests/test_gpu_r02.py / tests/test_shm_handler.py."""
 
 import numpy as np
 import pytest
