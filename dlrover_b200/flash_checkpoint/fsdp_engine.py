@@ -119,8 +119,21 @@ def _stage_items(files: List[Tuple[str, WriteItem]], planner: SavePlanner):
     no_shard: Dict[str, STORAGE_TYPES] = {}
     device_ranges, host_ranges, raw_chunks = [], [], []
     offset = 0
+    flat_sd = getattr(planner, "state_dict", None)
     for storage_key, item in files:
-        data = planner.resolve_data(item)
+        data = None
+        if item.type == WriteItemType.SHARD and flat_sd is not None:
+            # a DTensor's one local shard: skip the planner's lookup (to_local() through
+            # autograd + offset search, ~20 us per item, thousands of items per save)
+            obj = flat_sd.get(item.index.fqn)
+            local = getattr(obj, "_local_tensor", None) if obj is not None else None
+            if local is not None and item.tensor_data is not None and \
+                    tuple(local.shape) == tuple(item.tensor_data.chunk.sizes):
+                data = local
+        if data is None and item.type == WriteItemType.BYTE_IO:
+            data = getattr(planner, "_fc_resolved", {}).get(item.index.fqn)
+        if data is None:
+            data = planner.resolve_data(item)
         if torch.is_tensor(data):
             data = data.detach()
         if item.type != WriteItemType.SHARD:
@@ -198,6 +211,62 @@ def _write_memory_from_list(shm_handler=None, files=None, planner=None, blocking
     return results, no_shard, pending
 
 
+class NoShardData(dict):
+    """`no_shard_data` of a shard's meta: fqn -> object for every non-sharded entry of the
+    state dict (reference fsdp_engine.py:225-232).  Plain objects are ordinary dict items;
+    the tensor-valued entries (e.g. one `step` scalar per parameter) live in ONE bytes blob
+    + an index and are rebuilt on access — pickling a few hundred torch tensors one by one
+    costs tens of milliseconds per save, this costs microseconds."""
+
+    def __init__(self, plain=None, blob: bytes = b"", index=None):
+        super().__init__(plain or {})
+        self.blob = blob
+        self.index = dict(index or {})  # fqn -> (dtype, shape, offset, nbytes)
+
+    def __reduce__(self):
+        return (NoShardData, (dict(super().items()), self.blob, self.index))
+
+    def _tensor(self, fqn):
+        dtype, shape, off, n = self.index[fqn]
+        if n == 0:
+            return torch.empty(shape, dtype=dtype)
+        return torch.frombuffer(bytearray(self.blob[off:off + n]), dtype=dtype).reshape(shape)
+
+    def __getitem__(self, fqn):
+        if fqn in self.index:
+            return self._tensor(fqn)
+        return super().__getitem__(fqn)
+
+    def get(self, fqn, default=None):
+        try:
+            return self[fqn]
+        except KeyError:
+            return default
+
+    def __contains__(self, fqn):
+        return fqn in self.index or super().__contains__(fqn)
+
+    def __iter__(self):
+        yield from super().__iter__()
+        yield from self.index
+
+    def keys(self):
+        return list(self)
+
+    def items(self):
+        return [(k, self[k]) for k in self]
+
+    def values(self):
+        return [self[k] for k in self]
+
+    def __len__(self):
+        return super().__len__() + len(self.index)
+
+
+def no_shard_lookup(no_shard_data, fqn):
+    return no_shard_data[fqn]
+
+
 class _DeferredHostCopy:
     """The CUDA tensors among a plan's non-sharded objects, snapshotted with one
     device-side concatenation on the caller's stream; `get()` — called from the thread
@@ -205,20 +274,24 @@ class _DeferredHostCopy:
     the training thread never waits for a device-to-host copy."""
 
     def __init__(self, objects: Dict[str, Any]):
-        self._objects = dict(objects)
-        self._cuda = [(k, v) for k, v in objects.items() if torch.is_tensor(v) and v.is_cuda]
+        self._plain = {k: v for k, v in objects.items() if not torch.is_tensor(v)}
+        tensors = [(k, v.detach()) for k, v in objects.items() if torch.is_tensor(v)]
+        self._cuda = [(k, v) for k, v in tensors if v.is_cuda]
+        self._host = [(k, v) for k, v in tensors if not v.is_cuda]
         self._flat = self._event = None
         self._result: Optional[Dict[str, Any]] = None
         if self._cuda:
-            self._flat = torch.cat([v.detach().contiguous().reshape(-1).view(torch.uint8)
+            self._flat = torch.cat([v.contiguous().reshape(-1).view(torch.uint8)
                                     for _, v in self._cuda])
             self._event = torch.cuda.Event()
             self._event.record()
 
     def get(self) -> Dict[str, Any]:
+        """NoShardData: plain entries as they are, tensors packed into one blob."""
         if self._result is not None:
             return self._result
-        out = self._objects
+        out = dict(self._plain)
+        chunks, index, off = [], {}, 0
         if self._cuda:
             side = _copy_stream(self._flat.device)
             with torch.cuda.stream(side):
@@ -226,14 +299,19 @@ class _DeferredHostCopy:
                 host = self._flat.to("cpu", non_blocking=True)
                 self._flat.record_stream(side)
             side.synchronize()
-            off = 0
+            chunks.append(host.numpy().tobytes())
             for k, v in self._cuda:
                 n = v.numel() * v.element_size()
-                out[k] = host[off:off + n].clone().view(v.dtype).reshape(v.shape)
+                index[k] = (v.dtype, tuple(v.shape), off, n)
                 off += n
             self._flat = None
-        self._result = out
-        return out
+        for k, v in self._host:
+            raw = v.contiguous().reshape(-1).view(torch.uint8).numpy().tobytes()
+            index[k] = (v.dtype, tuple(v.shape), off, len(raw))
+            chunks.append(raw)
+            off += len(raw)
+        self._result = NoShardData(out, b"".join(chunks), index)
+        return self._result
 
 
 _copy_streams: Dict[int, "torch.cuda.Stream"] = {}
@@ -423,7 +501,7 @@ class SharedMemoryReader(StorageReader):
             pickled = False
             if not read_item.storage_index.offset:
                 # non-sharded entry: taken from the broadcast copy, not the segment
-                data = self.no_shard_data[read_item.storage_index.fqn]
+                data = no_shard_lookup(self.no_shard_data, read_item.storage_index.fqn)
                 if isinstance(data, io.BytesIO):
                     item_bytes = data
                 else:
@@ -557,8 +635,10 @@ class FsdpCheckpointEngine(CheckpointEngine):
         if torch.is_tensor(value):
             placements = getattr(value, "placements", None)
             if placements is not None:  # DTensor
-                local = value.to_local()
-                return ("D", tuple(value.shape), value.dtype, str(placements),
+                local = getattr(value, "_local_tensor", None)
+                if local is None:
+                    local = value.to_local()
+                return ("D", tuple(value.shape), value.dtype, placements,
                         tuple(local.shape), local.device.type)
             return ("T", tuple(value.shape), value.dtype, value.device.type)
         shards = getattr(value, "local_shards", None)
@@ -575,9 +655,13 @@ class FsdpCheckpointEngine(CheckpointEngine):
         flat = planner.state_dict
         key = [(k, self._describe(v)) for k, v in flat.items()]
         if cached_plan is not None:
+            resolved = {}
             for item in cached_plan.items:
                 if item.type == WriteItemType.BYTE_IO:
-                    key.append((item.index.fqn, planner.resolve_data(item).getbuffer().nbytes))
+                    data = planner.resolve_data(item)  # torch.save into a BytesIO: ~1 ms each
+                    resolved[item.index.fqn] = data
+                    key.append((item.index.fqn, data.getbuffer().nbytes))
+            planner._fc_resolved = resolved  # _stage_items takes them from here
         return key
 
     @timer

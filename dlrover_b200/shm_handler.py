@@ -126,7 +126,8 @@ class _Layout:
     """Result of one planning walk over a state_dict."""
 
     __slots__ = ("meta", "total", "device_leaves", "host_leaves", "leaf_metas", "reused",
-                 "extras", "shape_hash", "unchanged")
+                 "extras", "shape_hash", "unchanged", "dev_ptrs", "dev_dense", "dev_offs",
+                 "dev_lens")
 
     def __init__(self):
         self.meta: Any = None
@@ -138,6 +139,11 @@ class _Layout:
         self.extras: list = []  # non-tensor leaves, traversal order
         self.shape_hash = 0     # hash over the keys / container kinds met by the walk
         self.unchanged = False  # same meta tree as `prev` (keys, TensorMetas, extras)
+        # device leaves as the native layer wants them, gathered by the same walk
+        self.dev_ptrs: List[int] = []
+        self.dev_dense = True
+        self.dev_offs: List[int] = []
+        self.dev_lens: List[int] = []
 
 
 _IMMUTABLE_LEAVES = frozenset({int, float, str, bool, bytes, type(None), complex, torch.dtype,
@@ -160,6 +166,7 @@ def plan_layout(state_dict, prev: Optional["_Layout"] = None) -> _Layout:
     reused = 0
     shape_hash = 0
     extras = lay.extras
+    dev_ptrs, dev_offs, dev_lens = lay.dev_ptrs, lay.dev_offs, lay.dev_lens
 
     def walk(value):
         nonlocal total, reused, shape_hash
@@ -176,8 +183,16 @@ def plan_layout(state_dict, prev: Optional["_Layout"] = None) -> _Layout:
             metas.append(m)
             nbytes = m.numel * m.element_size
             if nbytes:
+                if value.is_cuda:
+                    dev.append((value, m))
+                    dev_ptrs.append(value.data_ptr())
+                    dev_offs.append(total)
+                    dev_lens.append(nbytes)
+                    if not value.is_contiguous():
+                        lay.dev_dense = False
+                else:
+                    host.append((value, m))
                 total += nbytes
-                (dev if value.is_cuda else host).append((value, m))
             return m
         kind = type(value)
         if kind is dict or (kind is not list and isinstance(value, Mapping)):
@@ -194,7 +209,11 @@ def plan_layout(state_dict, prev: Optional["_Layout"] = None) -> _Layout:
         # pickled later, possibly on the completion thread: mutable leaves (an args
         # Namespace, user objects) are copied NOW, on the calling thread, so they are
         # captured from the same iteration as the tensors
-        if kind not in _IMMUTABLE_LEAVES:
+        if kind is CheckpointConfig:
+            value = copy.copy(value)
+            if value.paths is not None:
+                value.paths = dict(value.paths)
+        elif kind not in _IMMUTABLE_LEAVES:
             try:
                 value = copy.deepcopy(value)
             except Exception:
@@ -450,6 +469,27 @@ def _row_ranges(t: torch.Tensor, off: int, max_rows: int = 1 << 16, min_row_byte
 
 def _triples(leaves):
     return [(t, m.offset, m.numel * m.element_size) for t, m in leaves]
+
+
+class _LeafRanges:
+    """(tensor, offset, nbytes) triples of a layout's device leaves, built only if
+    somebody iterates them (the common save already has the ptr/offset/length lists)."""
+
+    def __init__(self, leaves):
+        self._leaves = leaves
+
+    def __bool__(self):
+        return bool(self._leaves)
+
+    def __len__(self):
+        return len(self._leaves)
+
+    def __iter__(self):
+        return iter(_triples(self._leaves))
+
+    def __getitem__(self, i):
+        t, m = self._leaves[i]
+        return (t, m.offset, m.numel * m.element_size)
 
 
 def _clip_triples(triples, lo: int, hi: int):
@@ -1002,6 +1042,11 @@ class SharedMemoryHandler:
             self._stager = _DeviceStager(index)
         return self._stager
 
+    def _stager_for_ranges(self, device_ranges) -> _DeviceStager:
+        if isinstance(device_ranges, _LeafRanges):
+            return self._stager_for([t for t, _ in device_ranges._leaves])
+        return self._stager_for([r[0] for r in device_ranges])
+
     def ensure_segment(self, total: int):
         """Map a segment of exactly `total` bytes (re-creating it on a size
         change)."""
@@ -1022,7 +1067,8 @@ class SharedMemoryHandler:
                      pre_drain: Optional[Callable[[], None]] = None,
                      on_error: Optional[Callable[[], None]] = None,
                      in_place: Optional[bool] = None,
-                     window: Optional[Tuple[int, int]] = None, compact: bool = False):
+                     window: Optional[Tuple[int, int]] = None, compact: bool = False,
+                     prepared_hint=None):
         """Move bytes into the (already sized) segment.
 
         device_ranges / host_ranges: (tensor, segment offset, nbytes) for CUDA /
@@ -1080,10 +1126,11 @@ class SharedMemoryHandler:
         stager = None
         prepared = None
         if device_ranges:
-            stager = self._stager_for([r[0] for r in device_ranges])
+            stager = self._stager_for_ranges(device_ranges)
             # a dense repack of an oddly strided leaf runs on the CURRENT stream: do it
             # before a side stream is made to wait for that stream
-            prepared = stager.prepare_ranges(device_ranges, keepalive)
+            prepared = prepared_hint if prepared_hint is not None else \
+                stager.prepare_ranges(device_ranges, keepalive)
             if window is not None:
                 prepared = _clip_ranges(prepared, window[0], window[1])
                 if not prepared[0]:
