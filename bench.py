@@ -332,6 +332,16 @@ def run_ours(args):
     S = shapes.payload_bytes(sd)
     stream = torch.cuda.current_stream()
     ctx = native.get_context(local)
+    if os.getenv("BENCH_ONLY") == "coop" and world > 1:
+        # development shortcut (not the driver's contract): only the cooperative leg
+        ckpt.engine.close()
+        coop = measure_cooperative(args, sd, S, world, dev)
+        if rank == 0:
+            print(json.dumps({"metric": METRIC, "n_gpus": world, "only": "ddp_cooperative",
+                              "ddp_cooperative": coop}), flush=True)
+        dist.barrier()
+        dist.destroy_process_group()
+        return 0
 
     # ---- leg 1: raw C-ABI (value, roofline) ------------------------------------------
     import ctypes

@@ -103,10 +103,17 @@ class CoopContext:
         self.seq = base_seq + 1
         self.timeout = timeout
 
+    @classmethod
+    def slice_bytes(cls, total: int, n: int) -> int:
+        """Equal slices of ceil(total / n), rounded up to ALIGN: the save windows and the
+        slices of the cooperative restore (NCCL all-gather wants them equal) coincide, so
+        the part of the segment a rank has page-locked for saving is the part it reads on
+        restore."""
+        return (total + n * cls.ALIGN - 1) // (n * cls.ALIGN) * cls.ALIGN
+
     def window(self, total: int) -> Tuple[int, int]:
-        def cut(i):
-            return total if i >= self.n else (total * i // self.n) // self.ALIGN * self.ALIGN
-        return cut(self.index), cut(self.index + 1)
+        w = self.slice_bytes(total, self.n)
+        return min(total, self.index * w), min(total, (self.index + 1) * w)
 
 
 # ------------------------------------------------------------------- traversal --
@@ -1575,8 +1582,7 @@ class SharedMemoryHandler:
 
         index, n, group = coop
         total = self.shared_memory.size
-        align = CoopContext.ALIGN
-        w = (total + n * align - 1) // (n * align) * align   # equal slices (NCCL wants them equal)
+        w = CoopContext.slice_bytes(total, n)   # == the save windows
         stager.ctx.arena_reserve(n * w)
         lo, hi = min(total, index * w), min(total, (index + 1) * w)
         t0 = time.perf_counter()

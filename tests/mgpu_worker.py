@@ -286,7 +286,14 @@ def case_zero3(args, rank, world, dev, ckpt_dir):
     paths = {"model_states": os.path.join(ckpt_dir, "1000", f"zero_pp_rank_{rank}_model.pt"),
              "optim_states": os.path.join(ckpt_dir, "1000", f"zero_pp_rank_{rank}_optim.pt")}
     out = {"payload_bytes": 3 * numel * 4}
-    for step in (1000, 1001):
+    for step in (1000, 1001, 1002):
+        if step == 1001:
+            # the first save went through bounce slots and faulted the segment in; time the
+            # steady state (plain DMA into the page-locked segment) from here on
+            t0 = time.perf_counter()
+            out["pinned"] = bool(engine.wait_segment_pinned(600))
+            out["background_pin_s"] = time.perf_counter() - t0
+            dist.barrier()
         t0 = time.perf_counter()
         assert engine.save_to_memory(step, dict(state), paths)
         call_s = time.perf_counter() - t0
@@ -296,8 +303,10 @@ def case_zero3(args, rank, world, dev, ckpt_dir):
         assert engine.wait_memory_save(1800)
         total_s = time.perf_counter() - t0
         dist.barrier()
-        cmp_ = compare_with_oracle(engine._shm_handler, {**state, "_DLORVER_CKPT_CONFIG": None},
-                                   args.full_compare)
+        cmp_ = {}
+        if step != 1001 or args.full_compare:   # big states: check the first and the last save
+            cmp_ = compare_with_oracle(engine._shm_handler,
+                                       {**state, "_DLORVER_CKPT_CONFIG": None}, args.full_compare)
         out[f"step_{step}"] = {"call_s": call_s, "sources_frozen_s": frozen_s, "save_s": total_s,
                                "GBps": out["payload_bytes"] / total_s / 1e9,
                                "in_place": bool(engine._shm_handler.last_save_in_place),
@@ -364,7 +373,12 @@ def case_megatron(args, rank, world, dev, ckpt_dir):
     from dlrover_b200 import shapes as _s
 
     out = {"payload_bytes": _s.payload_bytes(state), "tp": tp, "pp": pp, "dp": dp}
-    for step in (20, 21):
+    for step in (20, 21, 22):
+        if step == 21:
+            t0 = time.perf_counter()
+            out["pinned"] = bool(engine.wait_segment_pinned(600))
+            out["background_pin_s"] = time.perf_counter() - t0
+            dist.barrier()
         model["iteration"] = step
         t0 = time.perf_counter()
         assert engine.save_to_memory(step, dict(state), paths)
@@ -372,12 +386,14 @@ def case_megatron(args, rank, world, dev, ckpt_dir):
         assert engine.wait_memory_save(1800)
         total_s = time.perf_counter() - t0
         dist.barrier()
-        cmp_ = compare_with_oracle(engine._shm_handler, {**state, "_DLORVER_CKPT_CONFIG": None},
-                                   args.full_compare)
+        cmp_ = {}
+        if step != 21 or args.full_compare:
+            cmp_ = compare_with_oracle(engine._shm_handler,
+                                       {**state, "_DLORVER_CKPT_CONFIG": None}, args.full_compare)
         out[f"step_{step}"] = {"call_s": call_s, "save_s": total_s,
                                "GBps": out["payload_bytes"] / total_s / 1e9, **cmp_}
     step, loaded = engine.load()
-    assert step == 21 and loaded["model_states"]["iteration"] == 21
+    assert step == 22 and loaded["model_states"]["iteration"] == 22
     del loaded
     dist.barrier()
     engine.close()

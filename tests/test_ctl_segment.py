@@ -91,7 +91,8 @@ def test_cooperative_handshake_and_slots(run_env):
         assert wins[0][0] == 0 and wins[-1][1] == total
         assert all(a[1] == b[0] for a, b in zip(wins, wins[1:]))
         assert all(w[0] % (2 << 20) == 0 for w in wins)
-        assert CoopContext(ctl, 1, 2, base).window(100) == (0, 100)  # tiny: all in the last slice
+        assert CoopContext(ctl, 0, 2, base).window(100) == (0, 100)  # tiny: all in the first slice
+        assert CoopContext(ctl, 1, 2, base).window(100) == (100, 100)
         with pytest.raises(TimeoutError):
             ctl.wait_coop_open(base + 1, timeout=0.05)
         threading.Timer(0.05, ctl.next_coop_seq).start()
