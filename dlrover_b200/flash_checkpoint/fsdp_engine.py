@@ -604,6 +604,33 @@ class FileReader(StorageReader):
         return True
 
 
+def _save_planner():
+    """torch's DefaultSavePlanner, minus one of its two full traversals of the state dict
+    when there is nothing for it to do: `_flatten_sharded_tensors` only rewrites nested
+    ShardedTensors (FSDP1 + TP); for DTensor / plain states it is a 4 ms no-op per save."""
+    from torch.distributed.checkpoint import default_planner as dp
+
+    class _Planner(dp.DefaultSavePlanner):
+        def set_up_planner(self, state_dict, storage_meta=None, is_coordinator=False):
+            try:
+                from torch.distributed._shard.sharded_tensor import ShardedTensor
+
+                if self.flatten_state_dict:
+                    state_dict, self.mappings = dp.flatten_state_dict(state_dict)
+                    if self.flatten_sharded_tensors and any(
+                            isinstance(v, ShardedTensor) for v in state_dict.values()):
+                        state_dict = dp._flatten_sharded_tensors(state_dict)
+                    self.state_dict = state_dict
+                    self.is_coordinator = is_coordinator
+                    return
+            except (ImportError, AttributeError):
+                pass
+            super().set_up_planner(state_dict=state_dict, storage_meta=storage_meta,
+                                   is_coordinator=is_coordinator)
+
+    return _Planner()
+
+
 def _dcp_save(state_dict, writer):
     if hasattr(dist_cp, "save"):
         return dist_cp.save(state_dict, storage_writer=writer)
@@ -678,9 +705,7 @@ class FsdpCheckpointEngine(CheckpointEngine):
         handler, writer = self._shm_handler, self._shm_writer
         pending = handler.pending_save()
         acquired = False if pending is not None else bool(self._shm_lock.acquire(blocking=False))
-        from torch.distributed.checkpoint.default_planner import DefaultSavePlanner
-
-        planner = DefaultSavePlanner()
+        planner = _save_planner()
         changed = True
         try:
             planner.set_up_planner(state_dict=state_dict, storage_meta=None,
