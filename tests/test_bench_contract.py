@@ -19,7 +19,9 @@ def _line(name):
 
 
 @pytest.mark.parametrize("name,n", [("r01_bench_n1.json", 1), ("r01_bench_n2.json", 2),
-                                    ("r01_bench_n4.json", 4), ("r01_bench_n8.json", 8)])
+                                    ("r01_bench_n4.json", 4), ("r01_bench_n8.json", 8),
+                                    ("r02_bench_n1_call3.json", 1), ("r02_bench_n2.json", 2),
+                                    ("r02_bench_n4_gpus0-3.json", 4), ("r02_bench_n8.json", 8)])
 def test_our_arm_line(name, n):
     d = _line(name)
     assert BASE_KEYS <= set(d), BASE_KEYS - set(d)
@@ -41,8 +43,28 @@ def test_our_arm_line(name, n):
         c = d["cpu_baseline"]
         assert {"value", "unit", "cores", "kind", "sample"} <= set(c) and c["kind"] == "port"
         assert d["stall_ms"]["async"] < 50.0                  # north_star: < 50 ms stall
+    if name.startswith("r02"):
+        assert r["traffic_source"].startswith("static:")      # a committed capture, says so
+        if n == 1:
+            fresh = d["restore_fresh_process"]
+            assert fresh["ours"]["bit_exact_probe"] and fresh["reference_style"]["bit_exact_probe"]
+            assert fresh["ours"]["restore_call_s"] < 1.0 < fresh["reference_style"]["restore_call_s"]
+        else:
+            coop = d["ddp_cooperative"]
+            assert coop["image_matches_replicas"] and coop["restore"]["bit_exact_spot_check"]
+            # n PCIe links instead of one: the ONE image lands faster than over a single link
+            assert coop["ms_per_save"] < coop["single_link_reference_policy_ms"]
+            if d.get("fsdp"):
+                assert d["fsdp"]["segment_matches_local_shards"]
     # whole-job aggregate: per-rank PCIe Gen5 x16 cannot exceed ~58 GB/s
     assert d["value"] / n < 58.0
+
+
+def test_reference_arm_runs_on_every_rank():
+    """The N-rank reference arm is like for like: every rank runs the reference's loop."""
+    d = _line("r02_bench_reference_n2.json")
+    assert d["impl"] == "reference" and d["n_gpus"] == 2 and d["ranks_run"] == 2
+    assert d["cpu_baseline"]["cores"] == 2
 
 
 def test_reference_arm_line():
