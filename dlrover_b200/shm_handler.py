@@ -1007,6 +1007,12 @@ class SharedMemoryHandler:
             self.wait_pending(timeout=120)
         except BaseException:
             pass
+        try:
+            # a background registration must not race the CUDA runtime's teardown
+            if self._stager is not None:
+                self._stager.detach()
+        except BaseException:
+            pass
 
     def wait_segment_pinned(self, timeout: float = 120.0) -> bool:
         """True once this process's window of the segment is page-locked (transfers are
