@@ -164,6 +164,17 @@ def case_fsdp(args, rank, world, dev, ckpt_dir):
     assert [s["reused_plan"] for s in out["saves"]] == [False, True, True], out["saves"]
     out["dict_sets"] = handler.metadata.dict_sets
     out["ctl_publishes"] = handler.metadata.ctl_publishes
+    # a structure change (one entry less) must be noticed on every rank: planned again once,
+    # reused afterwards; then back to the original structure for the reload below
+    smaller = {"model": dict(sd["model"]), "optim": sd["optim"]}
+    smaller["model"].pop(next(iter(smaller["model"])))
+    reuse = []
+    for step, tree in ((4, smaller), (5, smaller), (6, sd)):
+        assert engine.save_to_memory(step, tree, {"model_states": os.path.join(ckpt_dir, str(step))})
+        assert engine.wait_memory_save(300)
+        reuse.append(bool(engine.last_save_reused_plan))
+        dist.barrier()
+    assert reuse == [False, True, False], reuse
     # DCP-load back into zeroed shards (same sharding)
     tgt_factory = shapes.ShardedStateFactory(shp, world, rank, dev, mesh, seed=1)
     tgt_factory._wbuf.zero_()

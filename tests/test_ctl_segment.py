@@ -172,3 +172,82 @@ def test_without_a_control_segment_the_shared_dict_is_used(run_env, monkeypatch)
         trainer.close()
         agent.unlink()
         agent.close()
+
+
+def _coop_pair(agent, sd, step, fail_follower=False, monkeypatch=None):
+    """Leader + follower handlers of one process saving the same (CPU) state dict."""
+    import threading
+
+    ctl = agent.metadata.ctl
+    base = ctl.coop_seq()
+    leader, follower = SharedMemoryHandler(0, host=False), SharedMemoryHandler(0, host=False)
+    results = {}
+
+    def run(name, handler, index):
+        full = dict(sd)
+        full[DLROVER_CKPT_CONFIG_KEY] = CheckpointConfig(step=step, paths={})
+        coop = CoopContext(ctl, index, 2, base, timeout=5.0)
+        try:
+            if name == "follower" and fail_follower:
+                # its slice cannot be written
+                def boom(*a, **k):
+                    raise OSError("disk on fire")
+                handler.write_ranges = boom
+            handler.save_state_dict(full, blocking=True, coop=coop)
+            results[name] = "ok"
+        except BaseException as e:  # noqa: BLE001
+            results[name] = e
+
+    threads = [threading.Thread(target=run, args=("leader", leader, 0)),
+               threading.Thread(target=run, args=("follower", follower, 1))]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(30)
+    return leader, follower, results
+
+
+def test_cooperative_save_two_handlers_one_image(run_env):
+    agent = SharedMemoryHandler(0, host=True)
+    try:
+        sd = {"a": torch.arange(3 << 20, dtype=torch.float32), "n": 3,
+              "b": torch.arange(1 << 20, dtype=torch.int64)}
+        leader, follower, results = _coop_pair(agent, sd, step=4)
+        assert results == {"leader": "ok", "follower": "ok"}
+        back = agent.load_state_dict()
+        assert back[DLROVER_CKPT_CONFIG_KEY].step == 4
+        assert torch.equal(back["a"], sd["a"]) and torch.equal(back["b"], sd["b"]) and back["n"] == 3
+        # the two windows really were written by different handlers
+        total = leader.shared_memory.size
+        (a0, a1), (b0, b1) = (CoopContext(None, i, 2, 0).window(total) for i in (0, 1))
+        assert a0 == 0 and a1 == b0 and b1 == total and 0 < a1 < total
+        del back
+        leader.close()
+        follower.close()
+    finally:
+        agent.unlink()
+        agent.close()
+
+
+def test_cooperative_save_fails_as_a_whole_when_one_rank_fails(run_env):
+    """A follower that cannot write its slice reports it; the leader does NOT publish
+    writing_shm=False — the torn image stays marked as being written."""
+    agent = SharedMemoryHandler(0, host=True)
+    try:
+        sd = {"a": torch.arange(3 << 20, dtype=torch.float32)}
+        leader, follower, results = _coop_pair(agent, sd, step=1)
+        assert results == {"leader": "ok", "follower": "ok"}
+        leader.close()
+        follower.close()
+        sd["a"].add_(1)
+        leader, follower, results = _coop_pair(agent, sd, step=2, fail_follower=True)
+        assert isinstance(results["follower"], OSError)
+        assert isinstance(results["leader"], RuntimeError)      # "a local rank failed ..."
+        conf = agent.metadata.get()[DLROVER_CKPT_CONFIG_KEY]
+        assert conf.step == 2 and conf.writing_shm is True
+        assert agent.load_state_dict() == {}                    # nobody trusts the segment
+        leader.close()
+        follower.close()
+    finally:
+        agent.unlink()
+        agent.close()
