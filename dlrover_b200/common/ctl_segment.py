@@ -72,7 +72,9 @@ class ControlSegment:
     # -- lifecycle ----------------------------------------------------------------
     @classmethod
     def create(cls, shard_id: int, nbytes: int = DEFAULT_BYTES) -> "ControlSegment":
-        """Create (or adopt, if a previous agent left one) the shard's control segment."""
+        """Create the shard's control segment (re-initialising one a previous agent of the
+        same name left behind: like the reference's SharedDict, a new agent starts with no
+        meta — a leftover segment of an unrelated earlier job must not look loadable)."""
         name = ctl_name(shard_id)
         try:
             shm = SharedMemory(name=name, create=True, size=max(nbytes, META_OFFSET + (1 << 20)))
@@ -80,6 +82,12 @@ class ControlSegment:
         except FileExistsError:
             shm = SharedMemory(name=name)
             fresh = False
+            if shm.size < META_OFFSET + (1 << 20):  # left by something else: start over
+                shm.unlink()
+                shm.close()
+                shm = SharedMemory(name=name, create=True,
+                                   size=max(nbytes, META_OFFSET + (1 << 20)))
+                fresh = True
         seg = cls(shm)
         if fresh or seg._u64(_OFF_MAGIC) != MAGIC:
             struct.pack_into("<QQ", seg._buf, _OFF_VERSION, VERSION, 0)
@@ -87,6 +95,8 @@ class ControlSegment:
                         _OFF_CONF_LEN, _OFF_COOP_SEQ, _OFF_COOP_ABORT):
                 seg._put(off, 0)
             seg._put(_OFF_MAGIC, MAGIC)
+        else:
+            seg.clear()  # keeps the sequence numbers monotonic for attached readers
         return seg
 
     @classmethod
