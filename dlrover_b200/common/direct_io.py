@@ -18,8 +18,11 @@ backed by a block device the payload can bypass the page cache:
   * the bytes and their offsets are exactly the buffered writer's — files stay
     byte-identical (tests/test_direct_io.py compares sha256).
 
-`enabled_for(path)`: DLROVER_B200_DIRECT_IO=1 forces it, =0 disables it, "auto" (default)
-uses it when the directory is not on tmpfs/ramfs and an O_DIRECT probe write succeeds.
+`enabled_for(path)`: DLROVER_B200_DIRECT_IO=1 forces it (after a probe write), "auto" uses it on
+ext4 / xfs / btrfs / f2fs mounts, the default "0" leaves it off: on the GPU box of this project the
+checkpoint directory is an overlay file system, where O_DIRECT buys nothing (1.09 vs 1.08 GB/s
+including the final sync) and the buffered writer returns 3x sooner because 2 TB of page cache absorb
+the file (profiles/r02_persist.md) — how long the agent holds the shard lock is what matters there.
 """
 
 from __future__ import annotations
@@ -82,13 +85,13 @@ def _probe(dirpath: str) -> bool:
 
 
 def enabled_for(path: str) -> bool:
-    mode = os.getenv("DLROVER_B200_DIRECT_IO", "auto").strip().lower()
-    if mode in ("0", "false", "off"):
+    mode = os.getenv("DLROVER_B200_DIRECT_IO", "0").strip().lower()
+    if mode in ("0", "false", "off", ""):
         return False
     d = os.path.dirname(os.path.abspath(path)) or "."
     if mode in ("1", "true", "on"):
         return _probe(d)
-    return _fs_type(d) not in ("tmpfs", "ramfs", "") and _probe(d)
+    return _fs_type(d) in ("ext4", "ext3", "xfs", "btrfs", "f2fs") and _probe(d)
 
 
 def _addr(view: memoryview) -> int:

@@ -39,8 +39,14 @@ constexpr uint64_t kDmaPiece = 256ull << 20;        // restore fill memcpy size
 // stream of the process (a `loss.item()`!) starves until the whole checkpoint
 // has left the device (145-290 ms).  With exactly ONE piece in flight the
 // engine's queue empties for a moment after every piece and the foreign copy
-// goes through in ~0.4 ms, at 54.5 instead of 55.2 GB/s of drain throughput.
-// The pump thread therefore submits piece k+1 only after piece k completed.
-constexpr uint64_t kDrainPiece = 32ull << 20;
+// goes through after at most one piece.  The pump thread therefore submits piece
+// k+1 only after piece k completed.
+// Piece size (round 2, bench.py on one B200, profiles/r02_drain_modes.md): a
+// training loop with a `.item()` per step loses 9.2 ms per checkpoint with 32 MiB
+// pieces and 7.2 ms with 16 MiB pieces (each `.item()` issued during the 290 ms
+// drain waits for the piece in flight), for 55.1 vs 54.1 GB/s of checkpoint
+// throughput: the default favours the stall.  fc_set_drain /
+// DLROVER_B200_DRAIN_PIECE_MB change it.
+constexpr uint64_t kDrainPiece = 16ull << 20;
 constexpr int kDrainDepth = 1;
 constexpr int kDrainRing = 8;

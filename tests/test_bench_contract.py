@@ -20,7 +20,8 @@ def _line(name):
 
 @pytest.mark.parametrize("name,n", [("r01_bench_n1.json", 1), ("r01_bench_n2.json", 2),
                                     ("r01_bench_n4.json", 4), ("r01_bench_n8.json", 8),
-                                    ("r02_bench_n1_call3.json", 1), ("r02_bench_n2.json", 2),
+                                    ("r02_bench_n1_call3.json", 1), ("r02_bench_n1_final.json", 1),
+                                    ("r02_bench_n2.json", 2),
                                     ("r02_bench_n4_gpus0-3.json", 4), ("r02_bench_n8.json", 8)])
 def test_our_arm_line(name, n):
     d = _line(name)

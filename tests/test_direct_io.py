@@ -29,6 +29,8 @@ def test_mode_switch(tmp_path, monkeypatch):
     assert not direct_io.enabled_for(str(tmp_path / "x"))
     monkeypatch.setenv("DLROVER_B200_DIRECT_IO", "auto")
     assert not direct_io.enabled_for("/dev/shm/whatever")  # tmpfs: pointless
+    monkeypatch.delenv("DLROVER_B200_DIRECT_IO")
+    assert not direct_io.enabled_for(str(tmp_path / "x"))   # opt-in
 
 
 @pytest.mark.parametrize("nbytes", [1, 4095, 4096, 4097, (3 << 20) + 123, 40 << 20])
