@@ -35,7 +35,8 @@ def test_reference_unit_tests_pass_on_this_implementation():
     # the reference's tests leave their tiny segments behind ("unittest_ckpt_shm_0", ...)
     import glob
 
-    for leftover in glob.glob("/dev/shm/unittest_ckpt_shm_*") + glob.glob("/dev/shm/ckpt_shm_[0-9]"):
+    for leftover in glob.glob("/dev/shm/unittest_ckpt_shm_*") + glob.glob("/dev/shm/ckpt_shm_[0-9]") + \
+            glob.glob("/dev/shm/unittest_ckpt_ctl_*") + glob.glob("/dev/shm/ckpt_ctl_[0-9]"):
         try:
             os.unlink(leftover)
         except OSError:
