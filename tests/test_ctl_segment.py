@@ -251,3 +251,74 @@ def test_cooperative_save_fails_as_a_whole_when_one_rank_fails(run_env):
     finally:
         agent.unlink()
         agent.close()
+
+
+def test_oversized_meta_falls_back_to_the_shared_dict(run_env, monkeypatch):
+    """A tree that does not fit the control segment goes through the SharedDict (and the
+    control segment is cleared so that readers do not see an older tree)."""
+    agent = SharedMemoryHandler(0, host=True)
+    trainer = SharedMemoryHandler(0, host=False)
+    try:
+        _save(trainer, {"w": torch.zeros(8)}, 1)
+        assert trainer.metadata.ctl_publishes == 2 and trainer.metadata.dict_sets == 0
+        big = {"w": torch.zeros(8), "blob": "x" * (agent.metadata.ctl.meta_capacity + 10)}
+        _save(trainer, big, 2)
+        assert trainer.metadata.dict_sets == 2
+        back = agent.load_state_dict()
+        assert back[DLROVER_CKPT_CONFIG_KEY].step == 2 and len(back["blob"]) == len(big["blob"])
+        del back
+        _save(trainer, {"w": torch.ones(8)}, 3)          # fits again: back on the segment
+        assert agent.load_state_dict()[DLROVER_CKPT_CONFIG_KEY].step == 3
+        assert float(agent.load_state_dict()["w"][0]) == 1.0
+    finally:
+        trainer.close()
+        agent.unlink()
+        agent.close()
+
+
+def test_layout_fingerprint_notices_every_kind_of_change():
+    from dlrover_b200.shm_handler import plan_layout
+
+    def sd():
+        return {"m": {"a": torch.zeros(4, 3), "b": [torch.zeros(2), {"c": torch.zeros(5)}]},
+                "opt": {"lr": 0.1, "betas": (0.9, 0.95), "groups": [{"ids": [0, 1]}]},
+                DLROVER_CKPT_CONFIG_KEY: CheckpointConfig(step=1, paths={"m": "/p/1"})}
+
+    base = plan_layout(sd())
+    same = sd()
+    same[DLROVER_CKPT_CONFIG_KEY] = CheckpointConfig(step=2, paths={"m": "/p/2"})  # per save
+    assert plan_layout(same, base).unchanged
+    for mutate in (lambda d: d["m"].__setitem__("a", torch.zeros(4, 4)),        # shape
+                   lambda d: d["m"].__setitem__("a", torch.zeros(4, 3).half()),  # dtype
+                   lambda d: d["m"].__setitem__("z", d["m"].pop("a")),           # key renamed
+                   lambda d: d["m"]["b"].append(torch.zeros(1)),                 # list grew
+                   lambda d: d["opt"].__setitem__("lr", 0.05),                   # scalar leaf
+                   lambda d: d["opt"]["groups"][0].__setitem__("ids", [0, 2]),   # nested leaf
+                   lambda d: d["opt"].__setitem__("betas", (0.9, 0.99)),         # tuple leaf
+                   lambda d: d.__setitem__("extra", 1)):                         # new key
+        changed = sd()
+        mutate(changed)
+        assert not plan_layout(changed, base).unchanged, mutate
+    # mutable leaves are captured by value at plan time
+    live = sd()
+    lay = plan_layout(live)
+    live["opt"]["groups"][0]["ids"].append(99)
+    assert lay.meta["opt"]["groups"][0]["ids"] == [0, 1]
+
+
+def test_a_new_agent_starts_with_empty_meta(run_env):
+    first = SharedMemoryHandler(0, host=True)
+    trainer = SharedMemoryHandler(0, host=False)
+    try:
+        _save(trainer, {"w": torch.zeros(8)}, 5)
+        assert first.metadata.get()[DLROVER_CKPT_CONFIG_KEY].step == 5
+        first.close()                       # the agent process goes away, the segments stay
+        second = SharedMemoryHandler(0, host=True)
+        try:
+            assert second.metadata.get() == {} and second.no_checkpoint_state()
+            assert second.load_state_dict() == {}
+        finally:
+            second.unlink()
+            second.close()
+    finally:
+        trainer.close()
