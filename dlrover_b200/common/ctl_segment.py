@@ -230,6 +230,34 @@ class ControlSegment:
             delay = min(delay * 1.5, 0.001)
         return self._u64(_OFF_COOP_ABORT) == 0
 
+    # slot layout: +0 done_seq, +8 status, +16 arrived_seq, +24 ready
+    def slot_arrive(self, local_rank: int, seq: int, ready: bool):
+        """Follower: "I am in save number `seq`" (seq 0 withdraws), with whether it can
+        take part (no drain of its own still in flight)."""
+        off = HEADER_BYTES + SLOT_BYTES * local_rank
+        struct.pack_into("<Q", self._buf, off + 24, 1 if ready else 0)
+        struct.pack_into("<Q", self._buf, off + 16, seq)
+
+    def wait_arrivals(self, n_ranks: int, seq: int, timeout: float) -> Tuple[bool, bool]:
+        """Leader: wait until the local ranks 1..n-1 have arrived in save `seq`.
+        (all arrived, all ready)."""
+        deadline = time.time() + timeout
+        delay = 0.00005
+        while True:
+            arrived = ready = 0
+            for r in range(1, n_ranks):
+                off = HEADER_BYTES + SLOT_BYTES * r
+                a, rd = struct.unpack_from("<QQ", self._buf, off + 16)
+                if a == seq:
+                    arrived += 1
+                    ready += 1 if rd else 0
+            if arrived == n_ranks - 1:
+                return True, ready == n_ranks - 1
+            if time.time() > deadline:
+                return False, False
+            time.sleep(delay)
+            delay = min(delay * 1.5, 0.001)
+
     def slot_set(self, local_rank: int, step: int, ok: bool = True):
         off = HEADER_BYTES + SLOT_BYTES * local_rank
         struct.pack_into("<q", self._buf, off + 8, 0 if ok else SLOT_FAILED)

@@ -300,8 +300,8 @@ class CheckpointEngine(metaclass=ABCMeta):
         self._world_size = 1
         self._loader_group = None
         self._saver_group = None
-        self._coop_group = None
         self._coop_wanted = False
+        self._coop_established = False
         self._coop_ctl: Optional[ControlSegment] = None
         self._saving_ranks: Optional[List[int]] = None
         self._init_sync_group(comm_backend)
@@ -337,9 +337,6 @@ class CheckpointEngine(metaclass=ABCMeta):
             self._loader_group = dist.new_group(backend=backend, timeout=timedelta(seconds=60))
         self._saving_ranks = self.get_saving_ranks()
         self._coop_wanted = self._cooperative_by_config()
-        if self._coop_wanted and backend != default_backend:
-            # the cooperative save's readiness check spans ALL ranks
-            self._coop_group = dist.new_group(backend=backend, timeout=timedelta(seconds=60))
         self._node_group = None  # NCCL group of this node's ranks (cooperative restore)
         self._node_group_ok = False
         if self._coop_wanted and default_backend == "nccl":
@@ -437,6 +434,9 @@ class CheckpointEngine(metaclass=ABCMeta):
                 logger.info("No control segment (reference agent?): cooperative saves are off.")
                 self._coop_wanted = False
                 return False
+            if self._local_rank != 0:
+                # whatever a previous trainer of this rank left in the slot
+                self._coop_ctl.slot_arrive(self._local_rank, 0, False)
         return True
 
     def full_from_shards_supported(self) -> bool:
@@ -455,7 +455,10 @@ class CheckpointEngine(metaclass=ABCMeta):
         if not self.full_from_shards_supported():
             raise RuntimeError("save_shards_to_memory needs cooperative saves on a single node")
         conf = CheckpointConfig(step=step, paths=paths)
-        return self._cooperative_save(sharded_state_dict, conf, blocking, shards=True)
+        done = self._cooperative_save(sharded_state_dict, conf, blocking, shards=True)
+        if done is self._SOLO:
+            raise RuntimeError("save_shards_to_memory: the other local ranks do not take part")
+        return done
 
     def save_shards_to_storage(self, step, sharded_state_dict, paths: Dict[str, str],
                                blocking=False) -> bool:
@@ -472,9 +475,21 @@ class CheckpointEngine(metaclass=ABCMeta):
             self.latest_step = step
         return success
 
+    _SOLO = object()  # _cooperative_save: "not everybody takes part, use the reference policy"
+
     def _cooperative_save(self, state_dict, conf: CheckpointConfig, blocking: bool,
-                          shards: bool = False) -> bool:
-        handler = self._shm_handler
+                          shards: bool = False):
+        """The local ranks agree through the control segment — no collective: every
+        follower (local rank > 0) posts "I am in save number k, ready or not" in its slot
+        and waits for the leader's verdict; the leader (local rank 0, the reference's
+        saving rank) takes the shard lock, waits for the followers, settles readiness with
+        the leaders of the other nodes (the reference's all-reduce among saving ranks,
+        fc/engine.py:57-71) and opens the save or calls it off.
+
+        A job that calls save_checkpoint(MEMORY) on rank 0 only — legal with the reference,
+        whose other ranks return at once — is recognised by the followers not showing up:
+        the leader then saves alone, and keeps doing so."""
+        handler, ctl = self._shm_handler, self._coop_ctl
         local_world = env_utils.get_local_world_size()
         leader = self._local_rank == 0
         conf.rank = self._rank - self._local_rank  # the node's saving rank, as in the reference
@@ -485,32 +500,80 @@ class CheckpointEngine(metaclass=ABCMeta):
             pending.wait()
             pending = None
         ready = pending is None and bool(state_dict)
-        acquired = False
-        if leader and ready:
-            acquired = bool(self._shm_lock.acquire(blocking))
-            ready = acquired
-        base_seq = self._coop_ctl.coop_seq()
-        if not check_all_rank_ready(self._coop_group, ready):
-            self.is_skip = True
-            logger.info(f"Rank {self._rank} skips the cooperative save of step {conf.step}: not "
-                        "every rank is ready (the agent is persisting, or a drain is in flight).")
-            if acquired:
-                self._shm_lock.release()
-            return False
-        state_dict[DLROVER_CKPT_CONFIG_KEY] = conf
-        coop = CoopContext(self._coop_ctl, self._local_rank, local_world, base_seq,
-                           timeout=float(self._save_timeout))
+        seq = ctl.coop_seq() + 1
+        patience = float(self._save_timeout) if blocking else 60.0
 
-        def completed():
-            if acquired:
-                self._shm_lock.release()
+        if not leader:
+            ctl.slot_arrive(self._local_rank, seq, ready)
+            try:
+                go = ctl.wait_coop_open(seq, patience)
+            except TimeoutError:
+                ctl.slot_arrive(self._local_rank, 0, False)  # withdraw
+                logger.warning(f"Rank {self._rank}: the node's saving rank did not start save "
+                               f"{conf.step} within {patience:.0f}s; not taking part.")
+                return False
+            if not go or not ready:
+                self.is_skip = True
+                return False
+            state_dict[DLROVER_CKPT_CONFIG_KEY] = conf
+            coop = CoopContext(ctl, self._local_rank, local_world, seq - 1,
+                               timeout=float(self._save_timeout), opened=True)
+            if shards:
+                handler.save_shards_as_full(state_dict, coop,
+                                            blocking=not self._async_drain or blocking,
+                                            stream=self.snapshot_stream)
+            else:
+                handler.save_state_dict(state_dict, blocking=not self._async_drain or blocking,
+                                        stream=self.snapshot_stream, coop=coop)
+            self._cached_step = conf.step
+            return True
 
-        def failed():
-            # torn segment: writing_shm stays set; only the lock goes back
-            if acquired:
-                self._shm_lock.release()
-
+        # ---- leader ----
+        acquired = bool(self._shm_lock.acquire(blocking)) if ready else False
+        opened = False  # the save number has been consumed (opened or called off)
         try:
+            join = patience if self._coop_established else float(
+                os.getenv("DLROVER_B200_COOP_JOIN_TIMEOUT_S", "5"))
+            arrived, followers_ready = ctl.wait_arrivals(local_world, seq, join)
+            if not arrived:
+                logger.warning(
+                    f"Only rank {self._rank} of this node calls save_checkpoint (waited "
+                    f"{join:.0f}s for the other local ranks): saving alone from now on, as the "
+                    "reference does.")
+                ctl.next_coop_seq(aborted=True)
+                opened = True
+                self._coop_wanted = False
+                if acquired:
+                    self._shm_lock.release()
+                return self._SOLO
+            node_ready = acquired and followers_ready
+            all_ready = node_ready
+            if self._saver_group is not None and dist.get_world_size(self._saver_group) > 1:
+                # several nodes: their leaders settle it like the reference's saving ranks
+                all_ready = check_all_rank_ready(self._saver_group, node_ready)
+            if not all_ready:
+                ctl.next_coop_seq(aborted=True)
+                opened = True
+                self.is_skip = True
+                logger.info(f"Rank {self._rank} skips the cooperative save of step {conf.step}: "
+                            "not every rank is ready (the agent is persisting, or a drain is "
+                            "in flight).")
+                if acquired:
+                    self._shm_lock.release()
+                return False
+            state_dict[DLROVER_CKPT_CONFIG_KEY] = conf
+            coop = CoopContext(ctl, 0, local_world, seq - 1, timeout=float(self._save_timeout))
+
+            def completed():
+                if acquired:
+                    self._shm_lock.release()
+
+            def failed():
+                # torn segment: writing_shm stays set; only the lock goes back
+                if acquired:
+                    self._shm_lock.release()
+
+            opened = True  # the handler opens (or aborts) save `seq` from here on
             if shards:
                 handler.save_shards_as_full(state_dict, coop,
                                             blocking=not self._async_drain or blocking,
@@ -521,9 +584,12 @@ class CheckpointEngine(metaclass=ABCMeta):
                                         on_complete=completed, on_error=failed,
                                         stream=self.snapshot_stream, coop=coop)
         except BaseException:
+            if not opened:
+                ctl.next_coop_seq(aborted=True)  # nobody is left waiting
             if acquired and handler.pending_save() is None and self._shm_lock.locked():
                 self._shm_lock.release()
             raise
+        self._coop_established = True
         self._cached_step = conf.step
         return True
 
@@ -603,7 +669,9 @@ class CheckpointEngine(metaclass=ABCMeta):
         """Returns True when the state dict was (or is being) written to shared
         memory, False when this rank does not save or the save was skipped."""
         if self._cooperative():
-            return self._cooperative_save(state_dict, conf, blocking)
+            done = self._cooperative_save(state_dict, conf, blocking)
+            if done is not self._SOLO:
+                return done
         if not self._is_saving_rank():
             return False
         conf.rank = self._rank

@@ -97,11 +97,12 @@ class CoopContext:
     ALIGN = 2 << 20  # slice boundaries: 2 MiB (page- and huge-page-aligned windows)
 
     def __init__(self, ctl: ControlSegment, index: int, n: int, base_seq: int,
-                 timeout: float = 600.0):
+                 timeout: float = 600.0, opened: bool = False):
         self.ctl, self.index, self.n = ctl, index, n
         self.leader = index == 0
         self.seq = base_seq + 1
         self.timeout = timeout
+        self.opened = opened  # a follower that has already seen the leader open save `seq`
 
     @classmethod
     def slice_bytes(cls, total: int, n: int) -> int:
@@ -1418,7 +1419,7 @@ class SharedMemoryHandler:
                 raise
             coop.ctl.next_coop_seq()
         else:
-            if not coop.ctl.wait_coop_open(coop.seq, coop.timeout):
+            if not coop.opened and not coop.ctl.wait_coop_open(coop.seq, coop.timeout):
                 raise RuntimeError("cooperative save: the leader aborted")
             if total > 0:
                 self.attach_existing(total)

@@ -52,6 +52,29 @@ def _worker(rank, world, port, run_id, ckpt_dir, mode, out_dir):
             result["disk_ok"] = bool(torch.equal(mine["w"], sd["w"]))
             result["ready_all"] = bool(check_all_rank_ready(None, True))
             result["ready_one_not"] = bool(check_all_rank_ready(None, rank != 1))
+        elif mode == "rank0_only":
+            # legal with the reference: only rank 0 calls save_checkpoint(MEMORY), the other
+            # local ranks never show up -> the leader saves alone (after one short wait)
+            os.environ["DLROVER_B200_COOP_JOIN_TIMEOUT_S"] = "0.5"
+            ckpt = DdpCheckpointer(ckpt_dir)
+            eng = ckpt.engine
+            sd = {"w": torch.arange(3_000_000, dtype=torch.float32)}
+            if rank == 0:
+                t0 = time.time()
+                ckpt.save_checkpoint(1, sd, storage_type=StorageType.MEMORY)
+                ckpt.wait_memory_save()
+                result["first_s"] = time.time() - t0
+                sd["w"].add_(1)
+                t0 = time.time()
+                ckpt.save_checkpoint(2, sd, storage_type=StorageType.MEMORY)
+                ckpt.wait_memory_save()
+                result["second_s"] = time.time() - t0
+                result["coop_wanted_after"] = eng._coop_wanted
+            dist.barrier()
+            back = ckpt.load_checkpoint()      # every rank reads the node's one image
+            result["load_ok"] = bool(torch.equal(back["w"], torch.arange(
+                3_000_000, dtype=torch.float32) + 1))
+            del back
         elif mode == "cooperative":
             # replicated state, every local rank writes its slice of the ONE image
             ckpt = DdpCheckpointer(ckpt_dir)
@@ -169,6 +192,16 @@ def test_replicated_state_is_saved_cooperatively():
     # meta plane: no SharedDict.set at all, the control segment carries the saves
     assert r0["dict_sets"] == 0 and r0["ctl_publishes"] == 4   # 2 saves x (announce, finish)
     assert r1["dict_sets"] == 0 and r1["ctl_publishes"] == 0   # followers publish nothing
+
+
+@pytest.mark.timeout(300)
+def test_only_rank0_calling_save_does_not_hang():
+    """The cooperative default must not turn a rank-0-only save loop into a deadlock: the
+    leader notices that nobody joins, saves the whole image alone and stops waiting."""
+    r0, r1 = _run("rank0_only")
+    assert r0["load_ok"] and r1["load_ok"]
+    assert r0["coop_wanted_after"] is False
+    assert 0.4 < r0["first_s"] < 10 and r0["second_s"] < r0["first_s"]
 
 
 @pytest.mark.timeout(300)
