@@ -447,7 +447,7 @@ def run_ours(args):
     # ---- leg 3b: restore in a FRESH process (a restarted trainer), N=1 only ------------------
     fresh = None
     if world == 1:
-        fresh = measure_fresh_restore(ckpt, sd, S, ckpt_dir)
+        fresh = auxiliary(measure_fresh_restore, ckpt, sd, S, ckpt_dir)
 
     # ---- leg 4: cpu_baseline (rank 0, N=1 only) ------------------------------------------
     cpu_base = None
@@ -459,13 +459,13 @@ def run_ours(args):
     # ---- leg 5 (N>1): the SAME replicated state saved cooperatively -----------------------
     coop = None
     if world > 1:
-        coop = measure_cooperative(args, sd, S, world, dev)
+        coop = auxiliary(measure_cooperative, args, sd, S, world, dev)
     # ---- leg 6 (N>1): BASELINE configs[2] — FSDP full-shard, every rank its local shard ----
     fsdp = None
     if world > 1 and not os.getenv("BENCH_NO_FSDP"):
         del sd
         torch.cuda.empty_cache()
-        fsdp = measure_fsdp(args, world, rank, local, dev)
+        fsdp = auxiliary(measure_fsdp, args, world, rank, local, dev)
 
     if world > 1:
         dist.barrier()
@@ -508,6 +508,17 @@ def run_ours(args):
         dist.barrier()  # nothing else writes to stdout while rank 0 prints
         dist.destroy_process_group()
     return 0
+
+
+def auxiliary(leg, *a):
+    """The legs beyond the contract's line (cooperative, FSDP, fresh-process restore) must
+    not take the headline numbers down with them: a failure becomes an "error" record."""
+    try:
+        return leg(*a)
+    except Exception as e:  # noqa: BLE001
+        import traceback
+
+        return {"error": f"{type(e).__name__}: {e}", "where": traceback.format_exc()[-600:]}
 
 
 def measure_cooperative(args, sd, S, world, dev):
