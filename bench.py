@@ -627,6 +627,10 @@ def measure_fsdp(args, world, rank, local, dev):
     S_rank = factory.local_bytes
 
     def step(i):
+        # ranks leave the previous drain at slightly different times (36-40 GB/s per link):
+        # line them up like a training step's collectives would, so that `call` is the work
+        # of the call and not the wait for the slowest rank inside its readiness all-reduce
+        dist.barrier()
         t0 = time.perf_counter()
         ok = engine.save_to_memory(i, states[i & 1], {name: os.path.join(ckpt_dir, str(i))})
         call = time.perf_counter() - t0
@@ -674,7 +678,9 @@ def measure_fsdp(args, world, rank, local, dev):
            "payload_bytes_per_rank": S_rank, "payload_bytes_total": total,
            "ms_per_save": dt / args.steps * 1e3,
            "host_call_ms": sum(calls) / len(calls) * 1e3,
-           "host_call_ms_max": max(calls) * 1e3, "first_save_s": first,
+           "host_call_ms_max": max(calls) * 1e3,
+           "host_call_ms_slowest_rank": max_over_ranks(sum(calls) / len(calls), world, dev) * 1e3,
+           "first_save_s": first,
            "pack_ms": timings[0], "drain_ms": timings[1], "items_checked": checked,
            "segment_matches_local_shards": ok}
     drop_segment(engine)
