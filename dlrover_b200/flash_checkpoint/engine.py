@@ -530,7 +530,6 @@ class CheckpointEngine(metaclass=ABCMeta):
 
         # ---- leader ----
         acquired = bool(self._shm_lock.acquire(blocking)) if ready else False
-        opened = False  # the save number has been consumed (opened or called off)
         try:
             join = patience if self._coop_established else float(
                 os.getenv("DLROVER_B200_COOP_JOIN_TIMEOUT_S", "5"))
@@ -541,7 +540,6 @@ class CheckpointEngine(metaclass=ABCMeta):
                     f"{join:.0f}s for the other local ranks): saving alone from now on, as the "
                     "reference does.")
                 ctl.next_coop_seq(aborted=True)
-                opened = True
                 self._coop_wanted = False
                 if acquired:
                     self._shm_lock.release()
@@ -553,7 +551,6 @@ class CheckpointEngine(metaclass=ABCMeta):
                 all_ready = check_all_rank_ready(self._saver_group, node_ready)
             if not all_ready:
                 ctl.next_coop_seq(aborted=True)
-                opened = True
                 self.is_skip = True
                 logger.info(f"Rank {self._rank} skips the cooperative save of step {conf.step}: "
                             "not every rank is ready (the agent is persisting, or a drain is "
@@ -573,7 +570,8 @@ class CheckpointEngine(metaclass=ABCMeta):
                 if acquired:
                     self._shm_lock.release()
 
-            opened = True  # the handler opens (or aborts) save `seq` from here on
+            # the handler opens save `seq` once the segment has its size and the
+            # announcement is out
             if shards:
                 handler.save_shards_as_full(state_dict, coop,
                                             blocking=not self._async_drain or blocking,
@@ -584,8 +582,8 @@ class CheckpointEngine(metaclass=ABCMeta):
                                         on_complete=completed, on_error=failed,
                                         stream=self.snapshot_stream, coop=coop)
         except BaseException:
-            if not opened:
-                ctl.next_coop_seq(aborted=True)  # nobody is left waiting
+            if ctl.coop_seq() < seq:
+                ctl.next_coop_seq(aborted=True)  # wherever it failed: nobody is left waiting
             if acquired and handler.pending_save() is None and self._shm_lock.locked():
                 self._shm_lock.release()
             raise
