@@ -303,3 +303,49 @@ def test_user_views_stay_usable_while_the_dma_mapping_is_pinned_in_slices(cuda_d
     finally:
         handler.unlink()
         handler.close()
+
+
+def test_mapped_plan_compact_arena_scattered_segment_offsets(cuda_device):
+    """fc_plan_create_mapped: ranges scattered over a large segment, packed into an arena of
+    their own size (arena offset congruent to the source mod 16 -> bulk kernel), drained range
+    by range to their segment offsets; restore is the inverse.  What one rank of a "full
+    checkpoint from shards" save does."""
+    ctx = native.Context(0)
+    g = torch.Generator().manual_seed(17)
+    sizes = [5, 4096, 300_001, (2 << 20) + 3, 17, 1 << 20]
+    leaves = [torch.randint(0, 256, (n,), dtype=torch.uint8, generator=g).cuda() for n in sizes]
+    # segment offsets: far apart, odd alignments; holes belong to "other ranks"
+    host_offs, o = [], 1000
+    for n in sizes:
+        host_offs.append(o)
+        o += n + 777_777
+    total = o
+    arena_offs, a = [], 0
+    for t in leaves:
+        a += (t.data_ptr() - a) % 16
+        arena_offs.append(a)
+        a += t.numel()
+    ctx.arena_reserve(a)
+    plan = ctx.plan([t.data_ptr() for t in leaves], arena_offs, sizes, host_offsets=host_offs)
+    assert plan.arena_end == a and plan.payload_bytes == sum(sizes)
+    host = torch.full((total,), 7, dtype=torch.uint8).pin_memory()
+    stream = torch.cuda.current_stream()
+    ticket = plan.save_async(host.data_ptr(), stream)
+    ctx.save_wait(ticket)
+    want = np.full(total, 7, dtype=np.uint8)       # holes untouched
+    for t, off in zip(leaves, host_offs):
+        want[off:off + t.numel()] = oracle.tensor_bytes(t)
+    assert np.array_equal(host.numpy(), want)
+    keep = [t.clone() for t in leaves]
+    for direct in (False, True):
+        for t in leaves:
+            t.zero_()
+        plan.restore_async(host.data_ptr(), stream, direct=direct)
+        ctx.restore_wait()
+        for t, k in zip(leaves, keep):
+            assert torch.equal(t, k), direct
+    # a hybrid save needs the identity mapping
+    with pytest.raises(native.NativeError):
+        plan.save_hybrid_async(host.data_ptr(), host_offs[2], stream)
+    plan.destroy()
+    ctx.destroy()
