@@ -561,7 +561,9 @@ def get_context(device: int) -> Context:
             if not threads:
                 # first save / restart restore only; leave cores to the other local ranks
                 local_world = int(os.getenv("LOCAL_WORLD_SIZE", "1") or 1)
-                threads = max(2, min(16, (os.cpu_count() or 2) // max(1, 2 * local_world)))
+                # 8 is the measured sweet spot (profiles/r02_staged_and_pin.md: more threads
+                # fault a fresh segment in more slowly and copy no faster)
+                threads = max(2, min(8, (os.cpu_count() or 2) // max(1, 2 * local_world)))
             ctx.set_stage(threads, 0)
             _contexts[device] = ctx
         return ctx
