@@ -282,3 +282,31 @@ def test_forced_release_invalidates_the_old_holders_claim():
         b.close()
         owner.unlink()
         owner.close()
+
+
+def test_shared_memory_second_mapping_and_staleness():
+    """dma_address is a second mapping of the same object (the one that gets page-locked);
+    stale() notices a re-created or resized object behind the name."""
+    import ctypes
+    import uuid
+
+    from dlrover_b200.common.multi_process import SharedMemory
+
+    name = "twomaps" + uuid.uuid4().hex[:6]
+    a = SharedMemory(name=name, create=True, size=8192)
+    try:
+        assert a.dma_address != a.address and a.dma_address == a.dma_address
+        a.buf[100:104] = b"abcd"
+        assert ctypes.string_at(a.dma_address + 100, 4) == b"abcd"
+        ctypes.memmove(a.dma_address + 200, b"wxyz", 4)
+        assert bytes(a.buf[200:204]) == b"wxyz"
+        b = SharedMemory(name=name)
+        assert not a.stale() and not b.stale()
+        a.unlink()                                   # the writer re-creates it with another size
+        c = SharedMemory(name=name, create=True, size=4096)
+        assert b.stale() and not c.stale()
+        b.close()
+        c.unlink()
+        c.close()
+    finally:
+        a.close()
