@@ -456,58 +456,160 @@ def run_ours(args):
 
     drop_segment(ckpt.engine)
 
-    # ---- leg 5 (N>1): the SAME replicated state saved cooperatively -----------------------
-    coop = None
-    if world > 1:
-        coop = auxiliary(measure_cooperative, args, sd, S, world, dev)
-    # ---- leg 6 (N>1): BASELINE configs[2] — FSDP full-shard, every rank its local shard ----
-    fsdp = None
-    if world > 1 and not os.getenv("BENCH_NO_FSDP"):
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": raw_ms / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
+        "data": "synthetic", "config": workload_config(S, world, args.scale),
+        "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": e2e_ms / args.steps,
+                "h2d_bytes_per_step": 0, "d2h_bytes_per_step": S,
+                "api": "DdpCheckpointer.save_checkpoint(MEMORY)+wait_memory_save",
+                "first_save_s": first_save_s,
+                "background_pin_s": background_pin_s, "pinned": bool(pinned),
+                "note": "inputs of this path are the live device-resident parameters; "
+                        "the host buffer is the shm segment the drain fills"},
+        "stall_ms": stall,
+        "restore": restore,
+        "restore_fresh_process": fresh,
+        "ddp_cooperative": None,
+        "fsdp": None,
+        "roofline": {"bound": "hbm", "kernel": "fc_copy_tma<0> (gather/pack)",
+                     "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": ncu_traffic(),
+                     "traffic_source": "static: profiles/pack_kernel_ncu.json (one ncu --set "
+                                       "full capture of this kernel on this workload, "
+                                       "dram__bytes_read.sum + dram__bytes_write.sum)",
+                     "algorithmic_bytes_per_launch": 2 * S, "avg_launch_ms": pack_ms,
+                     "peak_source": peak_src},
+        "drain": {"avg_ms": drain_ms, "GBps": S / drain_ms / 1e6, "bound": "PCIe Gen5 x16"},
+        "cpu_baseline": cpu_base,
+        "gpu_launches": (k1 - k0) + (k3 - k2),
+        "dma_copies": m1 - m0,
+        "segment_pin_s": register_s,
+        "api_last_timings_ms": api_timings,
+        "clocks": clk,
+    }
+    if world == 1:
+        print(json.dumps(line), flush=True)
+        return 0
+
+    # The contract's numbers are complete here.  The two legs below (N>1) run under a
+    # deadline: whatever happens in them, rank 0 prints the line and every rank exits 0.
+    guard = AuxDeadline(rank, world, line)
+    guard.start()
+    # ---- leg 5: the SAME replicated state saved cooperatively ------------------------------
+    guard.run("ddp_cooperative", measure_cooperative, args, sd, S, world, dev)
+    # ---- leg 6: BASELINE configs[2] — FSDP full-shard, every rank its local shard -----------
+    if not os.getenv("BENCH_NO_FSDP"):
         del sd
         torch.cuda.empty_cache()
-        fsdp = auxiliary(measure_fsdp, args, world, rank, local, dev)
-
-    if world > 1:
-        dist.barrier()
-    if rank == 0:
-        line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": raw_ms / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
-            "data": "synthetic", "config": workload_config(S, world, args.scale),
-            "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": e2e_ms / args.steps,
-                    "h2d_bytes_per_step": 0, "d2h_bytes_per_step": S,
-                    "api": "DdpCheckpointer.save_checkpoint(MEMORY)+wait_memory_save",
-                    "first_save_s": first_save_s,
-                    "background_pin_s": background_pin_s, "pinned": bool(pinned),
-                    "note": "inputs of this path are the live device-resident parameters; "
-                            "the host buffer is the shm segment the drain fills"},
-            "stall_ms": stall,
-            "restore": restore,
-            "restore_fresh_process": fresh,
-            "ddp_cooperative": coop,
-            "fsdp": fsdp,
-            "roofline": {"bound": "hbm", "kernel": "fc_copy_tma<0> (gather/pack)",
-                         "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": ncu_traffic(),
-                         "traffic_source": "static: profiles/pack_kernel_ncu.json (one ncu --set "
-                                           "full capture of this kernel on this workload, "
-                                           "dram__bytes_read.sum + dram__bytes_write.sum)",
-                         "algorithmic_bytes_per_launch": 2 * S, "avg_launch_ms": pack_ms,
-                         "peak_source": peak_src},
-            "drain": {"avg_ms": drain_ms, "GBps": S / drain_ms / 1e6, "bound": "PCIe Gen5 x16"},
-            "cpu_baseline": cpu_base,
-            "gpu_launches": (k1 - k0) + (k3 - k2),
-            "dma_copies": m1 - m0,
-            "segment_pin_s": register_s,
-            "api_last_timings_ms": api_timings,
-            "clocks": clk,
-        }
-        print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.barrier()  # nothing else writes to stdout while rank 0 prints
-        dist.destroy_process_group()
+        guard.run("fsdp", measure_fsdp, args, world, rank, local, dev)
+    guard.park_if_failed()
+    dist.barrier()
+    guard.finish()  # prints on rank 0
+    dist.barrier()  # nothing else writes to stdout while rank 0 prints
+    dist.destroy_process_group()
     return 0
+
+
+class AuxDeadline:
+    """Keeps the legs beyond the contract's line (cooperative, FSDP) from taking the
+    headline numbers down with them.  They are full of collectives: a rank that fails
+    leaves the others waiting inside NCCL, where no exception can reach them.  So
+
+      * a failing rank records the error, drops a flag file and runs no further leg;
+      * a watcher thread on every rank ends the process (exit code 0) when the deadline
+        (BENCH_AUX_DEADLINE_S, default 300 s) passes or GRACE seconds after any rank's
+        flag appeared — rank 0 prints the line first, with what it has and an "error"
+        record for what is missing;
+      * when everything went well, finish() prints the line once."""
+
+    GRACE = 15.0
+
+    def __init__(self, rank: int, world: int, line: dict):
+        self.rank, self.world, self.line = rank, world, line
+        self.t_start = time.time()
+        self.deadline = self.t_start + float(os.getenv("BENCH_AUX_DEADLINE_S", "300"))
+        self.flags = (f"/tmp/fc_bench_flags_{os.getenv('TORCHELASTIC_RUN_ID', '')}_"
+                      f"{os.getenv('MASTER_PORT', '')}_{os.getppid()}")
+        self.lock = threading.Lock()
+        self.printed = False
+        self.failed = False
+        self.running = None
+
+    def start(self):
+        os.makedirs(self.flags, exist_ok=True)
+        threading.Thread(target=self._watch, daemon=True).start()
+
+    def run(self, key, leg, *a):
+        if self.failed:
+            return
+        self.running = key
+        rec = auxiliary(leg, *a)
+        with self.lock:
+            if not self.printed:
+                self.line[key] = rec
+        self.running = None
+        if isinstance(rec, dict) and "error" in rec:
+            self.failed = True
+            try:
+                open(os.path.join(self.flags, str(self.rank)), "w").close()
+            except OSError:
+                pass
+
+    def park_if_failed(self):
+        """A rank whose leg failed must not enter another collective: it waits here for
+        the watcher (which sees its flag) to end the process."""
+        while self.failed:
+            time.sleep(0.2)
+
+    def _emit(self, why):
+        with self.lock:
+            if self.printed:
+                return
+            self.printed = True
+            if self.rank == 0:
+                for key in ("ddp_cooperative", "fsdp"):
+                    if self.line.get(key) is None and (why or key == self.running):
+                        self.line[key] = {"error": why or "not run"}
+                print(json.dumps(self.line), flush=True)
+
+    def _flagged(self):
+        out = []
+        try:
+            for name in sorted(os.listdir(self.flags)):
+                try:  # a leftover of an older run with the same ids does not count
+                    if os.path.getmtime(os.path.join(self.flags, name)) >= self.t_start - 1.0:
+                        out.append(name)
+                except OSError:
+                    pass
+        except OSError:
+            pass
+        return out
+
+    def _watch(self):
+        # runs until the process ends: also after finish(), so that a rank waiting in the
+        # last barrier for one that the deadline took away does not sit out NCCL's timeout
+        first_flag = None
+        while True:
+            time.sleep(0.25)
+            now = time.time()
+            why = None
+            if now > self.deadline:
+                why = f"deadline: leg {self.running} still running after BENCH_AUX_DEADLINE_S"
+            else:
+                flagged = self._flagged()
+                if flagged:
+                    first_flag = first_flag or now
+                    if len(flagged) == self.world or now - first_flag > self.GRACE:
+                        why = f"leg abandoned: rank(s) {','.join(flagged)} failed in it"
+            if why:
+                self._emit(why)
+                sys.stdout.flush()
+                os._exit(0)
+
+    def finish(self):
+        self._emit(None)
 
 
 def auxiliary(leg, *a):
