@@ -17,9 +17,10 @@ into the node's POSIX shared-memory segment in the reference's byte layout.
   stall_ms  what the training loop loses per checkpoint (the other half of
          BASELINE.json's metric): measured with a synthetic matmul step.
   roofline  the gather (pack) kernel against the MEASURED copy bandwidth.
-  cpu_baseline / --impl reference: the reference's algorithm (per-tensor
-         blocking device->pageable-shm copy_, oracle/ref_port.py) on the same
-         box and state_dict.
+  cpu_baseline / --impl reference: the reference's memory save (per-tensor
+         blocking device->pageable-shm copy_) on the same box and state_dict —
+         the reference's own SharedMemoryHandler from oracle/_ref/pyref (kind
+         "reference"), else the restatement oracle/ref_port.py (kind "port").
 
 Launch: python bench.py [--gpus N --steps K --warmup W] ; for N>1 under
 torch.distributed.run, one rank per GPU, every rank saves its own 16 GB shard
@@ -165,26 +166,76 @@ def ncu_traffic():
 # ---------------------------------------------------------------- reference arm --
 
 
+
+def reference_saver(handler_rank: int, sample):
+    """The reference's own SharedMemoryHandler (byte code under oracle/_ref/pyref, built by
+    oracle/build_ref.py) when it is there, imports and gets through one save of `sample`;
+    otherwise the restatement oracle/ref_port.py.  Returns (saver, kind, why_not_reference)."""
+    why = None
+    try:
+        from oracle import ref_real
+
+        saver = ref_real.RealRefSaver(handler_rank)
+        try:
+            saver.save(sample)
+            return saver, "reference", None
+        except Exception:
+            try:
+                saver.close()
+            except Exception:
+                pass
+            raise
+    except Exception as e:  # noqa: BLE001
+        why = f"{type(e).__name__}: {e}"[:300]
+    from oracle.ref_port import RefPortSaver
+
+    saver = RefPortSaver(f"fc_bench_ref_{os.getpid()}_{handler_rank}")
+    saver.save(sample)
+    return saver, "port", why
+
+
+def reference_views(saver, kind):
+    """Tensors aliasing the segment the reference arm wrote (ckpt_saver.py:144-161)."""
+    return saver.views() if kind == "reference" else shm_layout_read(saver)
+
+
+REFERENCE_HOW = {
+    "reference": "the reference's own SharedMemoryHandler.save_state_dict (ckpt_saver.py:303-333, "
+                 "byte code compiled from the reference by oracle/build_ref.py)",
+    "port": "oracle/ref_port.py restating ckpt_saver.py:198-231,303-333",
+}
+
+
 def run_reference(args):
-    """Times the reference's algorithm (oracle/ref_port.py) on this box: EVERY rank
-    runs it on its own GPU and its own shard at the same time (as the reference does:
-    one blocking per-tensor copy loop per saving rank), the job's aggregate is
-    reported from the slowest rank's clock."""
+    """Times the reference's memory save on this box — the reference's own
+    SharedMemoryHandler when oracle/_ref/pyref holds its byte code, else the restatement
+    oracle/ref_port.py: EVERY rank runs it on its own GPU and its own shard at the same
+    time (as the reference does: one blocking per-tensor copy loop per saving rank), the
+    job's aggregate is reported from the slowest rank's clock."""
     rank, local, world = dist_env()
     import torch
     import torch.distributed as dist
 
     from dlrover_b200 import shapes
-    from oracle.ref_port import RefPortSaver
 
     if world > 1:
         dist.init_process_group("nccl")
+    os.environ.setdefault("TORCHELASTIC_RUN_ID", f"fcbenchref{os.getppid()}")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     sd = {"model_states": shapes.build_state_dict(
         shapes.scale_shapes(shapes.llama3_8b_shapes(), args.scale), torch.bfloat16, dev)}
     S = shapes.payload_bytes(sd)
-    saver = RefPortSaver(f"fc_bench_ref_{os.getpid()}")
+    saver, kind, why_port = reference_saver(200 + local, sd)  # first save: creates the segment
+    # one kind for the whole job: the reference itself only if every rank runs it
+    if world > 1 and sum_over_ranks(1.0 if kind == "reference" else 0.0, world, dev) != world \
+            and kind == "reference":
+        saver.close()
+        from oracle.ref_port import RefPortSaver
+
+        saver, kind, why_port = RefPortSaver(f"fc_bench_ref_{os.getpid()}"), "port", \
+            "another rank fell back to the port"
+        saver.save(sd)
     clocks = ClockSampler(local)
     try:
         for _ in range(max(args.warmup, 1)):
@@ -200,7 +251,7 @@ def run_reference(args):
         dt = max_over_ranks(dt_mine, world, dev)
         # restore the reference's way: CPU views on the (pageable) segment, one
         # H2D copy_ per tensor (ckpt_saver.py:144-161 + model.load_state_dict)
-        views = shm_layout_read(saver)
+        views = reference_views(saver, kind)
         barrier_sync(world)
         r0 = time.perf_counter()
         with torch.no_grad():
@@ -217,8 +268,8 @@ def run_reference(args):
         line = {
             "impl": "reference", "metric": METRIC, "value": gbs, "unit": UNIT, "n_gpus": world,
             "ranks_run": world,
-            "note": "the reference's memory-save path (oracle/ref_port.py) run on ALL ranks at "
-                    "once, each on its own GPU and shard; value = bytes of all ranks / slowest "
+            "note": f"the reference's memory-save path ({REFERENCE_HOW[kind]}) run on ALL ranks "
+                    "at once, each on its own GPU and shard; value = bytes of all ranks / slowest "
                     "rank's wall time",
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
@@ -230,12 +281,12 @@ def run_reference(args):
                         "reference_GBps": S * world / restore_s / 1e9,
                         "how": "frombuffer views on the pageable segment + per-tensor copy_ to "
                                "cuda, all ranks at once"},
-            "cpu_baseline": {"value": gbs, "unit": UNIT, "cores": world, "kind": "port",
-                             "host_cores": os.cpu_count(),
+            "cpu_baseline": {"value": gbs, "unit": UNIT, "cores": world, "kind": kind,
+                             "host_cores": os.cpu_count(), "fell_back_to_port_because": why_port,
                              "sample": f"{args.steps} full saves of the {S / 1e9:.2f} GB state_dict "
                                        f"on each of {world} rank(s): per-tensor blocking copy_ into "
                                        "a pageable /dev/shm segment, one host thread per rank "
-                                       "(oracle/ref_port.py restating ckpt_saver.py:198-231)"},
+                                       f"({REFERENCE_HOW[kind]})"},
             "e2e": {"value": gbs, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0, "clocks": clk,
         }
@@ -939,12 +990,9 @@ def measure_cpu_baseline(sd, S):
     """Reference algorithm on this box, bounded sample: 2 full saves."""
     import torch
 
-    from oracle.ref_port import RefPortSaver
-
-    saver = RefPortSaver(f"fc_bench_cpu_{os.getpid()}")
     wrapped = {"model_states": sd}
+    saver, kind, why_port = reference_saver(150, wrapped)  # creates + faults the pageable segment
     try:
-        saver.save(wrapped)  # creates + faults the pageable segment
         torch.cuda.synchronize()
         n = 2
         t0 = time.perf_counter()
@@ -955,11 +1003,11 @@ def measure_cpu_baseline(sd, S):
     finally:
         saver.close()
     return {"value": S / dt / 1e9, "unit": UNIT, "cores": 1, "host_cores": os.cpu_count(),
-            "kind": "port", "ms_per_step": dt * 1e3,
+            "kind": kind, "fell_back_to_port_because": why_port, "ms_per_step": dt * 1e3,
             "torch_save": measure_torch_save(sd),
-            "sample": "2 full saves of the same state_dict through oracle/ref_port.py: "
-                      "per-tensor blocking copy_ device->pageable /dev/shm "
-                      "(restates ckpt_saver.py:198-231); single host thread, as the reference"}
+            "sample": f"2 full saves of the same state_dict through {REFERENCE_HOW[kind]}: "
+                      "per-tensor blocking copy_ device->pageable /dev/shm; single host thread, "
+                      "as the reference"}
 
 
 def measure_torch_save(sd, budget_bytes=2 << 30):

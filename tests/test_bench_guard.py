@@ -96,3 +96,42 @@ def test_late_failure_keeps_what_rank0_measured(tmp_path):
     assert took < 20
     assert line["ddp_cooperative"] == {"value": 300.0}
     assert line["fsdp"] == {"value": 269.0}      # rank 0's own leg finished
+
+
+REF_CHILD = textwrap.dedent("""
+    import json, os, sys
+    sys.path.insert(0, {root!r})
+    os.environ["TORCHELASTIC_RUN_ID"] = "fcguardref%d" % os.getpid()
+    import torch
+    import bench
+    if sys.argv[1] == "hidden":
+        from oracle import ref_real
+        ref_real.PYREF = "/nonexistent/pyref"
+    sd = {{"model_states": {{"w": torch.arange(12, dtype=torch.float32).reshape(3, 4), "k": 5}}}}
+    saver, kind, why = bench.reference_saver(170, sd)
+    saver.save(sd)
+    views = bench.reference_views(saver, kind)
+    ok = torch.equal(views["model_states"]["w"], sd["model_states"]["w"])
+    del views
+    saver.close()
+    print("FCG " + json.dumps({{"kind": kind, "why": why, "ok": ok, "how": bench.REFERENCE_HOW[kind]}}))
+""")
+
+
+@pytest.mark.parametrize("mode", ["built", "hidden"])
+def test_reference_arm_uses_the_reference_itself_else_the_port(tmp_path, mode):
+    from oracle import build_ref, ref_real
+
+    if mode == "built" and not ref_real.available() and build_ref.build(verbose=False) == 0:
+        pytest.skip("oracle/_ref/pyref not built and no /root/reference here")
+    script = tmp_path / "child.py"
+    script.write_text(REF_CHILD.format(root=ROOT))
+    p = subprocess.run([sys.executable, str(script), mode], capture_output=True, text=True, timeout=300)
+    lines = [ln for ln in p.stdout.splitlines() if ln.startswith("FCG ")]
+    assert p.returncode == 0 and lines, p.stderr[-2000:]
+    rec = json.loads(lines[-1][4:])
+    assert rec["ok"]
+    if mode == "built":
+        assert rec["kind"] == "reference" and rec["why"] is None
+    else:
+        assert rec["kind"] == "port" and "ImportError" in rec["why"]

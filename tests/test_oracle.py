@@ -4,6 +4,7 @@ the known-answer values in the reference's tests."""
 
 import ctypes
 import hashlib
+import json
 import os
 import sys
 
@@ -129,3 +130,62 @@ def test_product_never_touches_the_oracle_or_the_reference():
                 if any(n == "oracle" or n.startswith("oracle.") for n in names):
                     offenders.append(path)
     assert not offenders, offenders
+
+
+_REAL_REF_CHILD = r"""
+import json, os, sys
+sys.path.insert(0, sys.argv[1])
+sys.path.insert(0, os.path.join(sys.argv[1], "tests", "golden"))
+os.environ["TORCHELASTIC_RUN_ID"] = "fcrealref%d" % os.getpid()
+import hashlib
+import torch
+import fixtures
+from oracle import ref_real
+from oracle.ref_port import RefPortSaver
+out = {"file": ref_real.load().__file__}
+for i, (name, build) in enumerate(fixtures.FIXTURES.items()):
+    sd = {"model_states": build()}
+    real = ref_real.RealRefSaver(160 + i)
+    port = RefPortSaver("fc_realref_%d_%d" % (os.getpid(), i))
+    try:
+        real.save(sd); real.save(sd)            # second save: the reference's cached-meta branch
+        port.save(sd)
+        a, b = bytes(real.buf), bytes(port.segment.buf)
+        back = real.views()["model_states"]
+        first = next((t for t in torch.utils._pytree.tree_leaves(back) if torch.is_tensor(t)), None)
+        out[name] = {"sha256": hashlib.sha256(a).hexdigest(), "bytes": len(a), "same_as_port": a == b,
+                     "views": first is not None}
+        del back, first
+    finally:
+        port.close(); real.close()
+left = [f for f in os.listdir("/dev/shm") if os.environ["TORCHELASTIC_RUN_ID"] in f]
+out["left_in_dev_shm"] = left
+print("FCREAL " + json.dumps(out))
+"""
+
+
+def test_compiled_reference_matches_goldens_and_port(tmp_path):
+    """oracle/_ref/pyref (the reference's own byte code, oracle/build_ref.py) is what the
+    bench's reference arm times when it is there: it leaves the golden images in its segment,
+    the same bytes as the port.  In a process of its own — other tests alias `dlrover.*`."""
+    import subprocess
+    import sys
+
+    from oracle import build_ref, ref_real
+
+    if not ref_real.available():
+        if build_ref.build(verbose=False) == 0:
+            pytest.skip("no /root/reference here and oracle/_ref/pyref not built")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    p = subprocess.run([sys.executable, "-c", _REAL_REF_CHILD, root], capture_output=True, text=True,
+                       timeout=300, cwd=str(tmp_path))
+    lines = [ln for ln in p.stdout.splitlines() if ln.startswith("FCREAL ")]
+    assert p.returncode == 0 and lines, p.stderr[-3000:]
+    out = json.loads(lines[-1][len("FCREAL "):])
+    assert os.sep + os.path.join("oracle", "_ref", "pyref") + os.sep in out["file"]
+    assert out["left_in_dev_shm"] == []
+    for name in fixtures.FIXTURES:
+        info, image = golden(name)
+        rec = out[name]
+        assert rec["bytes"] == image.size and rec["same_as_port"], name
+        assert rec["sha256"] == hashlib.sha256(image.tobytes()).hexdigest(), name
