@@ -66,7 +66,7 @@ def _gpus():
 
 
 @pytest.mark.gpu
-@pytest.mark.timeout(1500)
+@pytest.mark.timeout(700)
 @pytest.mark.parametrize("world", [2, 8])
 @pytest.mark.parametrize("case", CASES + ["fsdp_full"])
 def test_nccl_ranks_on_gpus(case, world):
@@ -76,7 +76,7 @@ def test_nccl_ranks_on_gpus(case, world):
     extra = ("--scale", str(1 / 32), "--flat-mib", "256")
     if case == "zero3":
         extra += ("--in-place", "--snapshot-mib", "300")
-    results = run_case(case, world, "nccl", "cuda", extra, timeout=1400)
+    results = run_case(case, world, "nccl", "cuda", extra, timeout=600)
     if case == "fsdp":
         assert all(r["fast_items"] and r["fast_items"] > 0 for r in results)  # DMA + scatter
     if case == "coop":
