@@ -14,6 +14,7 @@ import glob
 import json
 import os
 import shutil
+import signal
 import subprocess
 import sys
 import tempfile
@@ -37,14 +38,27 @@ def run_case(case, world, backend, device, extra=(), timeout=900):
     for k in ("ROLE_NAME", "TORCHELASTIC_RUN_ID", "RANK", "LOCAL_RANK", "WORLD_SIZE"):
         env.pop(k, None)
     try:
-        p = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=timeout)
+        # own session: a case that hangs is taken down with all its ranks (and their saver
+        # daemons), not just the launcher — nothing is left holding the GPUs
+        p = subprocess.Popen(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE,
+                             text=True, start_new_session=True)
+        try:
+            p.stdout_text, p.stderr_text = p.communicate(timeout=timeout)
+        except subprocess.TimeoutExpired:
+            try:
+                os.killpg(p.pid, signal.SIGKILL)
+            except ProcessLookupError:
+                pass
+            p.stdout_text, p.stderr_text = p.communicate()
+            raise AssertionError(f"{case} x{world} ({backend}): no result after {timeout}s\n"
+                                 f"{p.stderr_text[-2000:]}")
         results = [json.load(open(f)) for f in sorted(glob.glob(os.path.join(out, "rank*.json")))]
     finally:
         shutil.rmtree(out, ignore_errors=True)
     errors = [(r["rank"], r.get("error"), r.get("traceback", "")[-1500:]) for r in results
               if not r.get("ok")]
     assert p.returncode == 0 and len(results) == world and not errors, \
-        f"{case} x{world} ({backend}): rc={p.returncode} errors={errors}\n{p.stderr[-2000:]}"
+        f"{case} x{world} ({backend}): rc={p.returncode} errors={errors}\n{p.stderr_text[-2000:]}"
     return results
 
 
