@@ -147,3 +147,56 @@ def test_host_pack_and_unpack_match_the_oracle(sizes, gaps, threads, seed):
     native.host_unpack(got.ctypes.data, [t.ctypes.data if t.size else 0 for t in outs], offs,
                        list(sizes), threads)
     assert all(np.array_equal(x, y) for x, y in zip(outs, srcs))
+
+
+# ---------------------------------------------------------------- strided views --
+
+@st.composite
+def strided_views(draw):
+    """A view with arbitrary slicing (start/stop/step per dim) and an optional permutation of
+    a small base tensor — what `w[:, :k]`, `w[::2]`, `w.transpose(0, 1)[3:]` ... produce."""
+    ndim = draw(st.integers(1, 4))
+    shape = [draw(st.integers(1, 9)) for _ in range(ndim)]
+    dtype = draw(st.sampled_from([torch.uint8, torch.int16, torch.float32, torch.float64]))
+    n = 1
+    for s in shape:
+        n *= s
+    base = torch.arange(n, dtype=torch.int64).to(dtype).reshape(shape)
+    index = []
+    for s in shape:
+        start = draw(st.integers(0, s - 1))
+        stop = draw(st.integers(start + 1, s))
+        step = draw(st.integers(1, 3))
+        index.append(slice(start, stop, step))
+    view = base[tuple(index)]
+    if ndim > 1 and draw(st.booleans()):
+        view = view.permute(*draw(st.permutations(range(ndim))))
+    if draw(st.booleans()):  # a broadcast dim (stride 0): the same rows are read again
+        view = view.unsqueeze(0).expand(draw(st.integers(2, 3)), *view.shape)
+    return view
+
+
+@settings(max_examples=300, deadline=None)
+@given(view=strided_views(), off=st.integers(0, 1 << 40))
+def test_row_ranges_of_any_view_are_the_bytes_copy_would_deposit(view, off):
+    """shm_handler._row_ranges either declines (None: the caller repacks the leaf) or
+    returns ranges whose concatenation is exactly oracle.tensor_bytes(view) — the bytes the
+    reference's `shm_tensor.copy_(view)` leaves (ckpt_saver.py:228-231) — at consecutive
+    segment offsets starting at `off`."""
+    import ctypes
+
+    from dlrover_b200.shm_handler import _row_ranges
+
+    rows = _row_ranges(view, off, min_row_bytes=1)
+    if view.is_contiguous():
+        return  # the caller never asks for rows of a dense leaf
+    if rows is None:
+        return
+    want = oracle.tensor_bytes(view).tobytes()
+    got = b"".join(ctypes.string_at(p, n) for p, _, n in rows)
+    assert got == want
+    pos = off
+    for _, o, n in rows:
+        assert o == pos
+        pos += n
+    assert pos - off == view.numel() * view.element_size()
