@@ -200,3 +200,42 @@ def test_row_ranges_of_any_view_are_the_bytes_copy_would_deposit(view, off):
         assert o == pos
         pos += n
     assert pos - off == view.numel() * view.element_size()
+
+
+# ------------------------------------------------------- cooperative windows --
+
+@settings(max_examples=300, deadline=None)
+@given(total=st.integers(0, 1 << 36), n=st.integers(1, 16),
+       cuts=st.lists(st.integers(1, 1 << 30), min_size=0, max_size=12))
+def test_cooperative_windows_partition_the_image(total, n, cuts):
+    """CoopContext.window: the n local ranks' windows are consecutive, 2 MiB aligned (but
+    for the end of the image), cover [0, total) exactly once; clipping a list of ranges to
+    the windows and putting the pieces together gives the ranges back."""
+    from dlrover_b200.shm_handler import CoopContext, _clip_ranges
+
+    wins = [CoopContext(None, i, n, 0).window(total) for i in range(n)]
+    assert wins[0][0] == 0 and wins[-1][1] == total
+    for (a0, a1), (b0, b1) in zip(wins, wins[1:]):
+        assert a1 == b0 and a0 <= a1
+        assert a1 % (2 << 20) == 0 or a1 == total
+    # ranges laid back to back like a layout, with pseudo pointers
+    offs, lens, o = [], [], 0
+    for c in cuts:
+        if o + c > total:
+            break
+        offs.append(o)
+        lens.append(c)
+        o += c
+    ptrs = [0x7000_0000_0000 + 4096 * i + (o & 15) for i, o in enumerate(offs)]
+    pieces = {}
+    for lo, hi in wins:
+        for p, o, ln in zip(*_clip_ranges((ptrs, offs, lens), lo, hi)):
+            assert lo <= o and o + ln <= hi and ln > 0
+            i = max(k for k in range(len(offs)) if offs[k] <= o)
+            assert p - ptrs[i] == o - offs[i]            # pointer moved with the offset
+            pieces.setdefault(i, []).append((o, ln))
+    for i, (o, ln) in enumerate(zip(offs, lens)):
+        got = sorted(pieces.get(i, []))
+        assert got and got[0][0] == o and sum(x for _, x in got) == ln
+        for (a, la), (b, _) in zip(got, got[1:]):
+            assert a + la == b
