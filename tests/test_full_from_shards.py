@@ -130,3 +130,49 @@ def test_no_shard_data_round_trip():
     assert float(back["state.p3.step"]) == 3.0 and back["state.p3.step"].shape == ()
     assert back["param_groups"] == [{"lr": 0.1}] and back.get("missing", 7) == 7
     assert len(pickle.dumps(data)) < 1200   # a handful of tensors pickled by torch: ~10x that
+
+
+from hypothesis import given, settings  # noqa: E402
+from hypothesis import strategies as st  # noqa: E402
+
+
+@st.composite
+def _grids(draw):
+    """A tensor shape and a grid partition of it (cut points per dim) — DTensor Shard(d) on a
+    mesh, 2-D HSDP x TP style boxes, uneven last shards included."""
+    ndim = draw(st.integers(1, 3))
+    shape = [draw(st.integers(1, 12)) for _ in range(ndim)]
+    cuts = []
+    for s in shape:
+        k = draw(st.integers(0, min(3, s - 1)))
+        inner = sorted(draw(st.lists(st.integers(1, s - 1), min_size=k, max_size=k, unique=True))) \
+            if s > 1 else []
+        cuts.append([0] + inner + [s])
+    dtype = draw(st.sampled_from([torch.uint8, torch.bfloat16, torch.float32, torch.int64]))
+    return tuple(shape), cuts, dtype
+
+
+@settings(max_examples=200, deadline=None)
+@given(grid=_grids(), full_off=st.integers(0, 4096))
+def test_any_grid_of_boxes_tiles_the_full_tensor(grid, full_off):
+    """_box_ranges: painting every box of a grid partition at its place gives the bytes of the
+    gathered tensor (oracle.tensor_bytes) — each byte written exactly once."""
+    import itertools
+
+    shape, cuts, dtype = grid
+    n = int(np.prod(shape))
+    full = torch.arange(n, dtype=torch.int64).to(dtype).reshape(shape) if dtype != torch.bfloat16 \
+        else (torch.arange(n, dtype=torch.float32) % 251).to(torch.bfloat16).reshape(shape)
+    es = full.element_size()
+    image = np.zeros(full_off + n * es, dtype=np.uint8)
+    hits = np.zeros(full_off + n * es, dtype=np.uint8)
+    for corner in itertools.product(*[range(len(c) - 1) for c in cuts]):
+        lo = [cuts[d][i] for d, i in enumerate(corner)]
+        hi = [cuts[d][i + 1] for d, i in enumerate(corner)]
+        local = full[tuple(slice(a, b) for a, b in zip(lo, hi))].clone()
+        ranges = _box_ranges(local, tuple(lo), shape, full_off=full_off)
+        _paint(image, ranges)
+        for _, off, nb in ranges:
+            hits[off:off + nb] += 1
+    assert np.array_equal(image[full_off:], oracle.tensor_bytes(full))
+    assert bool((hits[full_off:] == 1).all()) and not image[:full_off].any()
