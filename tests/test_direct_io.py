@@ -92,3 +92,35 @@ def test_storage_write_uses_it_for_big_buffers(direct_dir, monkeypatch):
     p = str(direct_dir / "__0_0.distcp")
     storage.PosixDiskStorage().write(memoryview(data), p)
     assert open(p, "rb").read() == data.tobytes()
+
+
+def test_random_range_sets_with_small_pieces(direct_dir, monkeypatch):
+    """Many random layouts (gaps, odd offsets, odd source addresses, ranges smaller and
+    larger than a block) with the piece size shrunk to two blocks, so that every split of
+    DirectWriter.add / _put is taken: file == the bytes placed at their offsets; the direct
+    and buffered byte counts add up to what was queued."""
+    monkeypatch.setattr(direct_io, "PIECE", 2 * direct_io.BLOCK)
+    rng = np.random.default_rng(11)
+    blob = rng.integers(0, 256, size=1 << 20, dtype=np.uint8)
+    for case in range(40):
+        n_ranges = int(rng.integers(1, 9))
+        pos, want_parts = int(rng.integers(0, 9000)), []
+        for _ in range(n_ranges):
+            n = int(rng.choice([1, 17, 4095, 4096, 4097, 8192, 12_289, 40_000, 100_003]))
+            src = int(rng.integers(0, blob.size - n))
+            want_parts.append((pos, blob[src:src + n]))
+            pos += n + int(rng.choice([0, 1, 4096, 777]))
+        total = pos + int(rng.integers(0, 5000))
+        path = str(direct_dir / f"r{case}.bin")
+        w = direct_io.DirectWriter(path, total, threads=int(rng.integers(1, 5)))
+        want = np.zeros(total, dtype=np.uint8)
+        for off, piece in want_parts:
+            w.add(memoryview(piece), off)
+            want[off:off + piece.size] = piece
+        w.run()
+        w.close()
+        assert w.direct_bytes + w.buffered_bytes == sum(p.size for _, p in want_parts)
+        assert w.direct_bytes % direct_io.BLOCK == 0
+        got = np.fromfile(path, dtype=np.uint8)
+        assert np.array_equal(got, want), case
+        os.remove(path)
