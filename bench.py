@@ -661,6 +661,10 @@ class AuxDeadline:
 
     def finish(self):
         self._emit(None)
+        if self.rank == 0:
+            import shutil
+
+            shutil.rmtree(self.flags, ignore_errors=True)
 
 
 def auxiliary(leg, *a):

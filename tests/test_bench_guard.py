@@ -59,6 +59,10 @@ def _run(case, tmp_path, deadline="30"):
                               stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
              for r in range(2)]
     outs = [p.communicate(timeout=60) for p in procs]
+    import glob
+    import shutil
+    for d in glob.glob(f"/tmp/fc_bench_flags_{env['TORCHELASTIC_RUN_ID']}_*"):
+        shutil.rmtree(d, ignore_errors=True)
     assert [p.returncode for p in procs] == [0, 0], outs
     lines = [ln for ln in outs[0][0].splitlines() if ln.startswith("{")]
     assert len(lines) == 1, outs[0]
