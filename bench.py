@@ -503,7 +503,7 @@ def run_ours(args):
     # ---- leg 4: cpu_baseline (rank 0, N=1 only) ------------------------------------------
     cpu_base = None
     if world == 1:
-        cpu_base = measure_cpu_baseline(sd, S)
+        cpu_base = auxiliary(measure_cpu_baseline, sd, S)
 
     drop_segment(ckpt.engine)
 
